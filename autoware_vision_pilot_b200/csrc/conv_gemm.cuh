@@ -1,0 +1,43 @@
+// conv_gemm.cuh — host-side plan object for the tcgen05 implicit-GEMM convolution.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/vp_b200_ops.h"
+
+namespace vpb {
+
+// Kernel-side parameters (passed by value).
+struct ConvKParams {
+  int H, W, Cin, Cout;
+  int taps, phases;
+  int TH, TW, tw_shift;          // spatial tile (TH*TW == 128), log2(TW)
+  int BN;                        // N tile (multiple of 16, <= 256)
+  int tiles_h, tiles_w, tiles_n; // tile grid
+  int total_tiles;
+  int kchunks;                   // ceil(Cin / 64)
+  int stages;                    // smem pipeline depth
+  int act, mode, final_kind;
+  const float* bias;
+  void* out;
+  int ldo;
+  const void* res;
+  int ldr;
+  float* out_f32;
+  uint8_t* out_cls;
+};
+
+struct ConvPlan {
+  CUtensorMap mapA, mapB;
+  ConvKParams p;
+  int dtype;
+  int grid;
+  size_t smem_bytes;
+  double flops;  // algorithmic 2*MAC of this layer (for the roofline report)
+};
+
+int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan);
+int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream);
+int device_sm_count();
+
+}  // namespace vpb

@@ -1,0 +1,43 @@
+"""Helpers for the -m gpu parity tests: torch owns device memory, the C-ABI does the work."""
+import ctypes as C
+
+import torch
+
+from autoware_vision_pilot_b200 import _lib as L
+
+
+def tdtype(dtype):
+    return torch.bfloat16 if dtype == L.VPB_BF16 else torch.float16
+
+
+def conv_gemm(x_nhwc, w_tnc, bias, *, taps, phases=1, act=L.ACT_NONE, mode=L.EPI_STORE,
+              res=None, final_kind=L.FINAL_NONE, cout=None, ldo=None, bn=0, dtype=L.VPB_F16,
+              cin=None):
+    """x_nhwc [H,W,ldi] 16-bit cuda, w_tnc [taps*phases,Cout,Cin] 16-bit cuda, bias fp32 or None."""
+    H, W, ldi = x_nhwc.shape
+    T, Cout, Cin = w_tnc.shape
+    assert T == taps * phases
+    cin = Cin if cin is None else cin
+    Ho, Wo = (2 * H, 2 * W) if phases == 4 else (H, W)
+    a = L.ConvArgs()
+    a.dtype = dtype
+    a.H, a.W, a.Cin, a.ldi = H, W, cin, ldi
+    a.Cout, a.taps, a.phases = Cout, taps, phases
+    a.act, a.mode, a.final_kind = act, mode, final_kind
+    a.inp, a.w = x_nhwc.data_ptr(), w_tnc.data_ptr()
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.bn = bn
+    out = out_f32 = out_cls = None
+    if mode == L.EPI_FINAL:
+        out_f32 = torch.full((Cout, H, W), float("nan"), device="cuda", dtype=torch.float32)
+        out_cls = torch.full((H, W), 77, device="cuda", dtype=torch.uint8)
+        a.out_f32, a.out_cls = out_f32.data_ptr(), out_cls.data_ptr()
+    else:
+        ldo = ldo or (Cout + 7) // 8 * 8
+        out = torch.full((Ho, Wo, ldo), float("nan"), device="cuda", dtype=tdtype(dtype))
+        a.out, a.ldo = out.data_ptr(), ldo
+        if res is not None:
+            a.res, a.ldr = res.data_ptr(), res.shape[2]
+    L.check(L.lib().vpb_conv_gemm(C.byref(a), None), "vpb_conv_gemm")
+    torch.cuda.synchronize()
+    return out_f32, out_cls if mode == L.EPI_FINAL else None, out
