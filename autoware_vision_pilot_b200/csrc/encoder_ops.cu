@@ -1,0 +1,394 @@
+// encoder_ops.cu — the HBM-bound pieces of the EfficientNet-B0 encoder and of the context block.
+//
+// Reference: torchvision.models.efficientnet_b0(...).features as used by
+// Models/model_components/backbone.py:9-22 (third-party; architecture in SURVEY.md Appendix A),
+// Models/model_components/scene_context.py:25-57, backbone_feature_fusion.py:13-38.
+// The dense 1x1 convolutions of the encoder run on the tcgen05 GEMM (conv_gemm.cu); what is here
+// is byte-moving SIMT work: stem conv (3 input channels), depthwise convs with the
+// squeeze-excitation average pool fused in, the SE gate (folded into the projection weights),
+// global average pool, the context MLP (GEMV), the 1->128 conv on the 10x20 map and the max-pool
+// feature fusion.  All kernels read/write NHWC 16-bit with 16-byte vectors, accumulate in fp32.
+#include "common.cuh"
+#include "ops_internal.h"
+#include <algorithm>
+
+namespace vpb {
+
+// ------------------------------------------------------------------ stem conv 3x3 s2, 3 -> 32
+template <class E>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const uint2* __restrict__ in, int H, int W,
+                                                         const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         uint4* __restrict__ out, int Ho, int Wo) {
+  __shared__ float sw[27 * 32];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Ho * Wo) return;
+  const int oy = idx / Wo, ox = idx - oy * Wo;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = sb[i];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = 2 * oy - 1 + ky;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = 2 * ox - 1 + kx;
+      if (ix < 0 || ix >= W) continue;
+      const uint2 px = __ldg(in + static_cast<size_t>(iy) * W + ix);
+      const float2 a = unpack2<E>(px.x), b = unpack2<E>(px.y);
+      const float x[3] = {a.x, a.y, b.x};
+      const float* wt = sw + (ky * 3 + kx) * 3 * 32;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = fmaf(x[c], wt[c * 32 + i], acc[i]);
+    }
+  }
+  uint4* o = out + static_cast<size_t>(idx) * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 v;
+    v.x = pack2<E>(act_silu(acc[8 * j + 0]), act_silu(acc[8 * j + 1]));
+    v.y = pack2<E>(act_silu(acc[8 * j + 2]), act_silu(acc[8 * j + 3]));
+    v.z = pack2<E>(act_silu(acc[8 * j + 4]), act_silu(acc[8 * j + 5]));
+    v.w = pack2<E>(act_silu(acc[8 * j + 6]), act_silu(acc[8 * j + 7]));
+    o[j] = v;
+  }
+}
+
+// ------------------------------------------------------------------ depthwise + SiLU + SE pool
+DwGeom dw_geometry(int H, int W, int C, int k, int stride) {
+  DwGeom g;
+  const int pad = (k - 1) / 2;
+  g.Ho = (H + 2 * pad - k) / stride + 1;
+  g.Wo = (W + 2 * pad - k) / stride + 1;
+  g.G = C / 8;
+  g.PPB = std::max(1, 256 / g.G);
+  g.threads = g.G * g.PPB;
+  const int npix = g.Ho * g.Wo;
+  // ~4 waves of blocks over 148 SMs, each block a contiguous pixel range (multiple of PPB)
+  int ppb = (npix + 148 * 4 - 1) / (148 * 4);
+  ppb = (ppb + g.PPB - 1) / g.PPB * g.PPB;
+  g.pix_per_block = std::max(ppb, g.PPB);
+  g.nblocks = (npix + g.pix_per_block - 1) / g.pix_per_block;
+  return g;
+}
+
+template <class E, int K>
+__global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict__ in, int H, int W,
+                                                         int C, int stride, const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         uint4* __restrict__ out, int Ho, int Wo,
+                                                         long long* __restrict__ gap_acc, int G, int PPB,
+                                                         int pix_per_block) {
+  extern __shared__ float red[];  // [PPB][C]
+  constexpr int PAD = (K - 1) / 2;
+  const int cg = threadIdx.x % G, pl = threadIdx.x / G;
+  const int npix = Ho * Wo;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, npix);
+  float b8[8], sum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { b8[i] = __ldg(bias + cg * 8 + i); sum[i] = 0.f; }
+  for (int pix = p0 + pl; pix < p1; pix += PPB) {
+    const int oy = pix / Wo, ox = pix - oy * Wo;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = b8[i];
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * stride - PAD + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int ix = ox * stride - PAD + kx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 v = __ldg(in + (static_cast<size_t>(iy) * W + ix) * G + cg);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (ky * K + kx) * C + cg * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (ky * K + kx) * C + cg * 8 + 4));
+        const float2 x0 = unpack2<E>(v.x), x1 = unpack2<E>(v.y), x2 = unpack2<E>(v.z), x3 = unpack2<E>(v.w);
+        acc[0] = fmaf(x0.x, w0.x, acc[0]); acc[1] = fmaf(x0.y, w0.y, acc[1]);
+        acc[2] = fmaf(x1.x, w0.z, acc[2]); acc[3] = fmaf(x1.y, w0.w, acc[3]);
+        acc[4] = fmaf(x2.x, w1.x, acc[4]); acc[5] = fmaf(x2.y, w1.y, acc[5]);
+        acc[6] = fmaf(x3.x, w1.z, acc[6]); acc[7] = fmaf(x3.y, w1.w, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] = act_silu(acc[i]); sum[i] += acc[i]; }
+    uint4 o;
+    o.x = pack2<E>(acc[0], acc[1]); o.y = pack2<E>(acc[2], acc[3]);
+    o.z = pack2<E>(acc[4], acc[5]); o.w = pack2<E>(acc[6], acc[7]);
+    out[static_cast<size_t>(pix) * G + cg] = o;
+  }
+  // SE pooling sums, bit-reproducible: fixed-order reduction inside the block, then ONE 64-bit
+  // fixed-point (2^-24) integer atomic per channel — integer addition is order-independent, so
+  // the pooled mean does not depend on block scheduling.
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[pl * C + cg * 8 + i] = sum[i];
+  __syncthreads();
+  if (pl == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s = 0.f;
+      for (int q = 0; q < PPB; ++q) s += red[q * C + cg * 8 + i];
+      atomicAdd(reinterpret_cast<unsigned long long*>(gap_acc + cg * 8 + i),
+                static_cast<unsigned long long>(__float2ll_rn(s * 16777216.0f)));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ squeeze-excitation gate
+// Every block recomputes the (tiny) gate, then scales its slice of the projection weights.
+template <class E>
+__global__ void __launch_bounds__(256) se_scale_kernel(const long long* __restrict__ gap_acc,
+                                                        float inv_hw, int C, int sq,
+                                                        const float* __restrict__ w1,
+                                                        const float* __restrict__ b1,
+                                                        const float* __restrict__ w2,
+                                                        const float* __restrict__ b2,
+                                                        const float* __restrict__ w_proj, int Cout,
+                                                        typename E::T* __restrict__ w_scaled,
+                                                        float* __restrict__ scale_out) {
+  extern __shared__ float sm[];
+  float* mean = sm;        // [C]
+  float* hid = sm + C;     // [sq]
+  float* gate = hid + sq;  // [C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    mean[c] = static_cast<float>(static_cast<double>(gap_acc[c]) * (1.0 / 16777216.0)) * inv_hw;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < sq; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w1[static_cast<size_t>(j) * C + c], mean[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) hid[j] = act_silu(s + b1[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = b2[c];
+    for (int j = 0; j < sq; ++j) s = fmaf(w2[static_cast<size_t>(c) * sq + j], hid[j], s);
+    const float g = 1.0f / (1.0f + expf(-s));
+    gate[c] = g;
+    if (scale_out && blockIdx.x == 0) scale_out[c] = g;
+  }
+  __syncthreads();
+  const int total = Cout * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % C;
+    w_scaled[i] = from_f32<E>(w_proj[i] * gate[k]);
+  }
+}
+
+// ------------------------------------------------------------------ global average pool
+template <class E>
+__global__ void gap_kernel(const typename E::T* __restrict__ in, int HW, int C, int ld,
+                           float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += to_f32<E>(in[static_cast<size_t>(p) * ld + c]);
+  out[c] = s / static_cast<float>(HW);
+}
+
+// ------------------------------------------------------------------ GEMV: one warp per output
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x,
+                                                      const float* __restrict__ w,
+                                                      const float* __restrict__ b, int in_f, int out_f,
+                                                      int act, float* __restrict__ y) {
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= out_f) return;
+  const float* wr = w + static_cast<size_t>(o) * in_f;
+  float s = 0.f;
+  for (int i = lane; i < in_f; i += 32) s = fmaf(__ldg(wr + i), __ldg(x + i), s);
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  if (lane == 0) {
+    s += b[o];
+    if (act == ACT_GELU) s = act_gelu(s);
+    else if (act == ACT_SIGMOID) s = 1.0f / (1.0f + expf(-s));
+    else if (act == ACT_SILU) s = s / (1.0f + expf(-s));
+    y[o] = s;
+  }
+}
+
+// ------------------------------------------------------------------ context_layer_3 (1 -> Cout)
+template <class E>
+__global__ void ctx_conv1_kernel(const float* __restrict__ in, int H, int W,
+                                 const float* __restrict__ w, const float* __restrict__ b, int Cout,
+                                 typename E::T* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * W * Cout) return;
+  const int co = idx % Cout, pix = idx / Cout;
+  const int y = pix / W, x = pix - y * W;
+  float s = b[co];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int iy = y - 1 + ky, ix = x - 1 + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) s = fmaf(in[iy * W + ix], w[co * 9 + ky * 3 + kx], s);
+    }
+  out[idx] = from_f32<E>(act_gelu(s));
+}
+
+// ------------------------------------------------------------------ max-pool feature fusion
+// One warp per (output pixel, source tensor, 8-channel group): lanes split the pooling window,
+// then a shuffle max.  Window = 2^n x 2^n (n successive MaxPool2d(2,2)).
+template <class E>
+__global__ void __launch_bounds__(256) fuse_pool_kernel(const uint4* __restrict__ f0,
+                                                         const uint4* __restrict__ f1,
+                                                         const uint4* __restrict__ f2,
+                                                         const uint4* __restrict__ f3,
+                                                         const uint4* __restrict__ f4, int H4, int W4,
+                                                         uint4* __restrict__ out) {
+  // channel-group layout of the output pixel: [f0:4 | f1:3 | f2:5 | f3:10 | f4:160] = 182 groups
+  constexpr int kGroups = 182;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= H4 * W4 * kGroups) return;
+  const int g = gw % kGroups, pix = gw / kGroups;
+  const int y = pix / W4, x = pix - y * W4;
+  const uint4* src; int win, G, cg;
+  if (g < 4) { src = f0; win = 16; G = 4; cg = g; }
+  else if (g < 7) { src = f1; win = 8; G = 3; cg = g - 4; }
+  else if (g < 12) { src = f2; win = 4; G = 5; cg = g - 7; }
+  else if (g < 22) { src = f3; win = 2; G = 10; cg = g - 12; }
+  else { src = f4; win = 1; G = 160; cg = g - 22; }
+  const int Ws = W4 * win;
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+  for (int t = lane; t < win * win; t += 32) {
+    const int wy = t / win, wx = t - wy * win;
+    const uint4 v = __ldg(src + (static_cast<size_t>(y * win + wy) * Ws + (x * win + wx)) * G + cg);
+    const float2 a = unpack2<E>(v.x), b = unpack2<E>(v.y), c = unpack2<E>(v.z), d = unpack2<E>(v.w);
+    m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], b.x); m[3] = fmaxf(m[3], b.y);
+    m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], d.x); m[7] = fmaxf(m[7], d.y);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], o));
+  if (lane == 0) {
+    uint4 o;
+    o.x = pack2<E>(m[0], m[1]); o.y = pack2<E>(m[2], m[3]);
+    o.z = pack2<E>(m[4], m[5]); o.w = pack2<E>(m[6], m[7]);
+    out[static_cast<size_t>(pix) * kGroups + g] = o;
+  }
+}
+
+}  // namespace vpb
+
+// ====================================================================== C-ABI launchers
+using namespace vpb;
+#define DISPATCH(dtype, KERNEL, ...)           \
+  do {                                         \
+    if ((dtype) == VPB_BF16) KERNEL<BF16> __VA_ARGS__; \
+    else KERNEL<F16> __VA_ARGS__;              \
+  } while (0)
+
+extern "C" int vpb_stem_conv(int dtype, const void* in, int H, int W, const float* w,
+                             const float* bias, void* out, void* stream) {
+  const int Ho = H / 2, Wo = W / 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = Ho * Wo;
+  if (dtype == VPB_BF16)
+    stem_conv_kernel<BF16><<<(n + 127) / 128, 128, 0, st>>>(static_cast<const uint2*>(in), H, W, w, bias,
+                                                           static_cast<uint4*>(out), Ho, Wo);
+  else
+    stem_conv_kernel<F16><<<(n + 127) / 128, 128, 0, st>>>(static_cast<const uint2*>(in), H, W, w, bias,
+                                                          static_cast<uint4*>(out), Ho, Wo);
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}
+
+extern "C" int vpb_depthwise(int dtype, const void* in, int H, int W, int C, int k, int stride,
+                             const float* w, const float* bias, void* out, long long* gap_acc,
+                             void* stream) {
+  if ((C & 7) || (k != 3 && k != 5) || (stride != 1 && stride != 2) || C > 2048) {
+    vpb_set_error("depthwise: unsupported C=%d k=%d stride=%d", C, k, stride);
+    return VPB_ERR_ARG;
+  }
+  const DwGeom g = dw_geometry(H, W, C, k, stride);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(g.PPB) * C * sizeof(float);
+  const uint4* i4 = static_cast<const uint4*>(in);
+  uint4* o4 = static_cast<uint4*>(out);
+#define DW_LAUNCH(E, K)                                                                          \
+  depthwise_kernel<E, K><<<g.nblocks, g.threads, smem, st>>>(i4, H, W, C, stride, w, bias, o4, g.Ho, \
+                                                             g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block)
+  if (dtype == VPB_BF16) { if (k == 3) DW_LAUNCH(BF16, 3); else DW_LAUNCH(BF16, 5); }
+  else { if (k == 3) DW_LAUNCH(F16, 3); else DW_LAUNCH(F16, 5); }
+#undef DW_LAUNCH
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}
+
+extern "C" int vpb_se_scale(int dtype, const long long* gap_acc, int HW, int C, int sq,
+                            const float* w1, const float* b1, const float* w2, const float* b2,
+                            const float* w_proj, int Cout, void* w_scaled, float* scale_out,
+                            void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = (2 * static_cast<size_t>(C) + sq) * sizeof(float);
+  const int grid = std::max(1, std::min(32, (Cout * C + 8191) / 8192));
+  if (dtype == VPB_BF16)
+    se_scale_kernel<BF16><<<grid, 256, smem, st>>>(gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
+                                                   w_proj, Cout, static_cast<__nv_bfloat16*>(w_scaled),
+                                                   scale_out);
+  else
+    se_scale_kernel<F16><<<grid, 256, smem, st>>>(gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
+                                                  w_proj, Cout, static_cast<__half*>(w_scaled), scale_out);
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}
+
+extern "C" int vpb_gap(int dtype, const void* in, int HW, int C, int ld, float* out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == VPB_BF16)
+    gap_kernel<BF16><<<(C + 127) / 128, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(in), HW, C, ld, out);
+  else
+    gap_kernel<F16><<<(C + 127) / 128, 128, 0, st>>>(static_cast<const __half*>(in), HW, C, ld, out);
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}
+
+extern "C" int vpb_linear(const float* x, const float* w, const float* b, int in_f, int out_f, int act,
+                          float* y, void* stream) {
+  linear_kernel<<<(out_f + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, b, in_f, out_f, act, y);
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}
+
+extern "C" int vpb_ctx_conv1(int dtype, const float* in, int H, int W, const float* w, const float* b,
+                             int Cout, void* out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = H * W * Cout;
+  if (dtype == VPB_BF16)
+    ctx_conv1_kernel<BF16><<<(n + 255) / 256, 256, 0, st>>>(in, H, W, w, b, Cout, static_cast<__nv_bfloat16*>(out));
+  else
+    ctx_conv1_kernel<F16><<<(n + 255) / 256, 256, 0, st>>>(in, H, W, w, b, Cout, static_cast<__half*>(out));
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}
+
+extern "C" int vpb_fuse_pool_concat(int dtype, const void* f0, const void* f1, const void* f2,
+                                    const void* f3, const void* f4, int H4, int W4, void* out,
+                                    void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long warps = static_cast<long>(H4) * W4 * 182;
+  const int blocks = static_cast<int>((warps * 32 + 255) / 256);
+#define FP_ARGS static_cast<const uint4*>(f0), static_cast<const uint4*>(f1), static_cast<const uint4*>(f2), \
+                static_cast<const uint4*>(f3), static_cast<const uint4*>(f4), H4, W4, static_cast<uint4*>(out)
+  if (dtype == VPB_BF16) fuse_pool_kernel<BF16><<<blocks, 256, 0, st>>>(FP_ARGS);
+  else fuse_pool_kernel<F16><<<blocks, 256, 0, st>>>(FP_ARGS);
+#undef FP_ARGS
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}

@@ -1,0 +1,785 @@
+// engine.cu — host side of the B200 camera-perception engine (C++; owns weights, buffers, the
+// per-frame launch list and its CUDA graph) behind the C-ABI of include/vp_b200.h.
+//
+// Reference composition being replaced (paths relative to the reference repo):
+//   SceneSegNetwork.forward   Models/model_components/scene_seg_network.py:24-29
+//   Scene3DNetwork.forward    scene_3d_network.py:25-31   (frozen encoder shared with SceneSeg)
+//   DomainSegNetwork.forward  domain_seg_network.py:17-20 (frozen encoder+context+neck shared)
+//   EgoLanesNetwork.forward   ego_lanes_network.py:30-37  (own encoder, 1456-ch fused features)
+// One engine evaluates 1..4 of these per frame.  Sub-graphs whose weights are byte-identical
+// across the loaded checkpoints (FNV-1a over the fp32 tensors) are evaluated once.
+#include "common.cuh"
+#include "conv_gemm.cuh"
+#include "ops_internal.h"
+#include "../../include/vp_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace vpb {
+
+// =============================================================== weight file (.vpw)
+// magic "VPW1", u32 n; per tensor: u32 name_len, name, u32 dtype (0 f32, 1 i64), u32 ndim,
+// u32 dims[ndim], u64 nbytes, raw little-endian data.  Written by
+// autoware_vision_pilot_b200/weights.py from the reference's .pth state_dict.
+struct HostTensor {
+  std::vector<int> dims;
+  std::vector<float> f;
+  size_t numel() const { size_t n = 1; for (int d : dims) n *= d; return n; }
+};
+using WeightMap = std::map<std::string, HostTensor>;
+
+static int load_vpw(const char* path, WeightMap& out) {
+  FILE* fp = fopen(path, "rb");
+  if (!fp) { vpb_set_error("cannot open weight file '%s'", path); return VPB_ERR_IO; }
+  auto fail = [&](const char* why) { fclose(fp); vpb_set_error("%s: %s", path, why); return VPB_ERR_IO; };
+  char magic[4]; uint32_t n = 0;
+  if (fread(magic, 1, 4, fp) != 4 || memcmp(magic, "VPW1", 4) != 0) return fail("not a VPW1 file");
+  if (fread(&n, 4, 1, fp) != 1 || n > 100000) return fail("bad tensor count");
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t nl = 0, dt = 0, nd = 0; uint64_t nb = 0;
+    if (fread(&nl, 4, 1, fp) != 1 || nl > 4096) return fail("bad name length");
+    std::string name(nl, '\0');
+    if (fread(&name[0], 1, nl, fp) != nl) return fail("truncated name");
+    if (fread(&dt, 4, 1, fp) != 1 || fread(&nd, 4, 1, fp) != 1 || nd > 8) return fail("bad header");
+    HostTensor t; t.dims.resize(nd);
+    for (uint32_t d = 0; d < nd; ++d) { uint32_t v; if (fread(&v, 4, 1, fp) != 1) return fail("bad dims"); t.dims[d] = static_cast<int>(v); }
+    if (fread(&nb, 8, 1, fp) != 1) return fail("bad size");
+    const size_t ne = t.numel();
+    if (dt == 0) {
+      if (nb != ne * 4) return fail("f32 size mismatch");
+      t.f.resize(ne);
+      if (ne && fread(t.f.data(), 4, ne, fp) != ne) return fail("truncated data");
+    } else {
+      if (fseek(fp, static_cast<long>(nb), SEEK_CUR) != 0) return fail("truncated data");  // num_batches_tracked: ignored
+    }
+    out[name] = std::move(t);
+  }
+  fclose(fp);
+  return VPB_OK;
+}
+
+static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+static uint64_t hash_prefix(const WeightMap& w, const std::string& pfx) {
+  uint64_t h = 1469598103934665603ull;
+  for (const auto& kv : w) {
+    if (kv.first.compare(0, pfx.size(), pfx) != 0) continue;
+    const std::string local = kv.first.substr(pfx.size());
+    h = fnv1a(h, local.data(), local.size());
+    h = fnv1a(h, kv.second.f.data(), kv.second.f.size() * 4);
+  }
+  return h;
+}
+
+// =============================================================== engine
+struct Tens {  // NHWC 16-bit activation, channel stride == C
+  void* p = nullptr; int H = 0, W = 0, C = 0;
+  size_t bytes() const { return static_cast<size_t>(H) * W * C * 2; }
+};
+
+struct OpRec {
+  std::string name;
+  std::function<int(cudaStream_t)> launch;
+  double flops = 0;
+  bool gemm = false;
+};
+
+struct ModelOut {
+  int kind = 0, C = 0, H = 0, W = 0;
+  float* d_raw = nullptr; uint8_t* d_cls = nullptr;
+  float* h_raw = nullptr; uint8_t* h_cls = nullptr;
+  bool has_cls = false;
+};
+
+struct Prefixes { std::string enc, ctx, neck, head; };
+static Prefixes prefixes_for(int kind) {
+  switch (kind) {
+    case VP_SCENE_SEG: return {"Backbone.encoder.", "SceneContext.", "SceneNeck.", "SceneSegHead."};
+    case VP_SCENE_3D: return {"PreTrainedBackbone.pretrainedBackBone.encoder.", "DepthContext.", "DepthNeck.", "SuperDepthHead."};
+    case VP_DOMAIN_SEG: return {"DomainSegUpstream.pretrainedBackBone.encoder.", "DomainSegUpstream.pretrainedContext.", "DomainSegUpstream.pretrainedNeck.", "DomainSegHead."};
+    default: return {"BEVBackbone.encoder.", "AutoSteerContext.", "EgopathNeck.", "EgoLanesHead."};
+  }
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+struct vp_engine {
+  vp_engine_config cfg{};
+  int dtype = VPB_F16;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<void*> dev_allocs;
+  std::vector<void*> host_allocs;
+  size_t weight_bytes = 0, act_bytes = 0;
+  std::vector<OpRec> ops;                 // network ops (after the pre-process)
+  std::vector<std::unique_ptr<ConvPlan>> plans;
+  PreprocessPlan pre;
+  uint8_t* d_frame = nullptr; size_t d_frame_cap = 0;
+  uint8_t* h_frame = nullptr; size_t h_frame_cap = 0;
+  void* d_pre = nullptr;                  // [320][640][4]
+  uint8_t* d_resized = nullptr;           // optional uint8 resized image (tap "resized")
+  std::vector<ModelOut> outs;
+  std::map<std::string, Tens> taps;
+  int shared_encoders = 0, shared_trunks = 0;
+  // SE pooling accumulators of every MBConv block: one arena, zeroed by one memset per frame
+  long long* d_gap = nullptr; size_t gap_used = 0;
+  static constexpr size_t kGapCap = 64 * 1024;   // int64 slots (16 blocks x <=1152 ch per encoder)
+  long long* gap_alloc(int C) {
+    if (!d_gap) d_gap = static_cast<long long*>(dalloc(kGapCap * 8, false));
+    if (gap_used + C > kGapCap) return nullptr;
+    long long* p = d_gap + gap_used;
+    gap_used += (C + 31) / 32 * 32;
+    return p;
+  }
+  // graph
+  cudaGraphExec_t gexec = nullptr;
+  int g_h = 0, g_w = 0, g_stride = 0; const uint8_t* g_src = nullptr;
+  // module caches for sharing
+  struct EncOut { Tens f[5]; };
+  std::map<uint64_t, EncOut> enc_cache;
+  std::map<uint64_t, Tens> trunk_cache;    // hash(enc)+hash(ctx)+hash(neck) -> neck output
+
+  ~vp_engine() {
+    if (gexec) cudaGraphExecDestroy(gexec);
+    for (void* p : dev_allocs) cudaFree(p);
+    for (void* p : host_allocs) cudaFreeHost(p);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+
+  // ---------------------------------------------------------- allocation / upload helpers
+  void* dalloc(size_t bytes, bool is_weight) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(bytes, 256)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, std::max<size_t>(bytes, 256));
+    dev_allocs.push_back(p);
+    (is_weight ? weight_bytes : act_bytes) += bytes;
+    return p;
+  }
+  Tens act_alloc(int H, int W, int C) {
+    Tens a; a.H = H; a.W = W; a.C = C;
+    a.p = dalloc(a.bytes(), false);
+    return a;
+  }
+  float* upload_f32(const std::vector<float>& v) {
+    float* p = static_cast<float*>(dalloc(v.size() * 4, true));
+    if (p) cudaMemcpy(p, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
+    return p;
+  }
+  void* upload_16(const std::vector<float>& v) {
+    std::vector<uint16_t> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+      if (dtype == VPB_BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v[i]); memcpy(&h[i], &b, 2); }
+      else { __half b = __float2half_rn(v[i]); memcpy(&h[i], &b, 2); }
+    }
+    void* p = dalloc(h.size() * 2, true);
+    if (p) cudaMemcpy(p, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
+    return p;
+  }
+
+  // ---------------------------------------------------------- op emitters
+  int add_conv(const std::string& name, const Tens& in, int Cout, int taps, int phases, const void* w,
+               const float* bias, int act, int mode, const Tens* out, const Tens* res,
+               int final_kind = 0, float* out_f32 = nullptr, uint8_t* out_cls = nullptr) {
+    vpb_conv_args a{};
+    a.dtype = dtype; a.H = in.H; a.W = in.W; a.Cin = in.C; a.ldi = in.C;
+    a.Cout = Cout; a.taps = taps; a.phases = phases; a.act = act; a.mode = mode;
+    a.final_kind = final_kind; a.in = in.p; a.w = w; a.bias = bias;
+    if (out) { a.out = out->p; a.ldo = out->C; }
+    if (res) { a.res = res->p; a.ldr = res->C; }
+    a.out_f32 = out_f32; a.out_cls = out_cls;
+    auto plan = std::make_unique<ConvPlan>();
+    int rc = conv_plan_build(&a, plan.get());
+    if (rc != VPB_OK) return rc;
+    ConvPlan* pp = plan.get();
+    plans.push_back(std::move(plan));
+    OpRec op; op.name = name; op.flops = pp->flops; op.gemm = true;
+    op.launch = [pp](cudaStream_t s) { return conv_plan_launch(pp, s); };
+    ops.push_back(std::move(op));
+    return VPB_OK;
+  }
+  void add_op(const std::string& name, std::function<int(cudaStream_t)> fn, double flops = 0) {
+    OpRec op; op.name = name; op.launch = std::move(fn); op.flops = flops;
+    ops.push_back(std::move(op));
+  }
+};
+
+namespace vpb {
+
+#define NEED(w, key)                                                             \
+  auto it_##__LINE__ = (w).find(key);                                            \
+  if (it_##__LINE__ == (w).end()) { vpb_set_error("weight '%s' missing", std::string(key).c_str()); return VPB_ERR_IO; }
+
+static const HostTensor* find_w(const WeightMap& w, const std::string& key) {
+  auto it = w.find(key);
+  if (it == w.end()) { vpb_set_error("weight '%s' missing from checkpoint", key.c_str()); return nullptr; }
+  return &it->second;
+}
+
+// BatchNorm folding (eval mode, eps 1e-5 — torchvision EfficientNet-B0): y = conv(x)*s + t
+static bool bn_fold(const WeightMap& w, const std::string& p, int C, std::vector<float>& s, std::vector<float>& t) {
+  const HostTensor *g = find_w(w, p + "weight"), *b = find_w(w, p + "bias"),
+                   *m = find_w(w, p + "running_mean"), *v = find_w(w, p + "running_var");
+  if (!g || !b || !m || !v) return false;
+  s.resize(C); t.resize(C);
+  for (int c = 0; c < C; ++c) {
+    const float sc = g->f[c] / std::sqrt(v->f[c] + 1e-5f);
+    s[c] = sc; t[c] = b->f[c] - m->f[c] * sc;
+  }
+  return true;
+}
+
+// Conv2d weight [Cout][Cin][k][k] -> [k*k][Cout][Cin] (optionally scaled per Cout)
+static std::vector<float> pack_conv(const HostTensor& t, const std::vector<float>* scale) {
+  const int Cout = t.dims[0], Cin = t.dims[1], k = t.dims[2];
+  std::vector<float> o(t.f.size());
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int tt = 0; tt < k * k; ++tt)
+        o[(static_cast<size_t>(tt) * Cout + co) * Cin + ci] =
+            t.f[(static_cast<size_t>(co) * Cin + ci) * k * k + tt] * (scale ? (*scale)[co] : 1.0f);
+  return o;
+}
+// ConvTranspose2d weight [Cin][Cout][2][2] -> [a*2+b][Cout][Cin]
+static std::vector<float> pack_convT(const HostTensor& t) {
+  const int Cin = t.dims[0], Cout = t.dims[1];
+  std::vector<float> o(t.f.size());
+  for (int ci = 0; ci < Cin; ++ci)
+    for (int co = 0; co < Cout; ++co)
+      for (int ph = 0; ph < 4; ++ph)
+        o[(static_cast<size_t>(ph) * Cout + co) * Cin + ci] = t.f[(static_cast<size_t>(ci) * Cout + co) * 4 + ph];
+  return o;
+}
+
+static const int kStages[7][6] = {  // expand, kernel, stride, cin, cout, repeats
+    {1, 3, 1, 32, 16, 1}, {6, 3, 2, 16, 24, 2}, {6, 5, 2, 24, 40, 2}, {6, 3, 2, 40, 80, 3},
+    {6, 5, 1, 80, 112, 3}, {6, 5, 2, 112, 192, 4}, {6, 3, 1, 192, 320, 1}};
+
+// ---------------------------------------------------------------- encoder (backbone.py:11-22)
+static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p, const std::string& tag,
+                         vp_engine::EncOut& out) {
+  const int dt = e.dtype;
+  std::vector<float> s, t;
+  // stem
+  const HostTensor* sw = find_w(w, p + "0.0.weight");
+  if (!sw || !bn_fold(w, p + "0.1.", 32, s, t)) return VPB_ERR_IO;
+  std::vector<float> stem(27 * 32);
+  for (int co = 0; co < 32; ++co)
+    for (int c = 0; c < 3; ++c)
+      for (int k = 0; k < 9; ++k) stem[(k * 3 + c) * 32 + co] = sw->f[(co * 3 + c) * 9 + k] * s[co];
+  float* d_stem = e.upload_f32(stem);
+  float* d_stem_b = e.upload_f32(t);
+  Tens x = e.act_alloc(kNetH / 2, kNetW / 2, 32);
+  {
+    const void* in = e.d_pre; void* o = x.p;
+    e.add_op(tag + "stem", [=](cudaStream_t st) { return vpb_stem_conv(dt, in, kNetH, kNetW, d_stem, d_stem_b, o, st); },
+             2.0 * x.H * x.W * 32 * 27);
+  }
+  Tens stage_out[9];
+  stage_out[0] = x;
+  for (int si = 0; si < 7; ++si) {
+    const int exp = kStages[si][0], k = kStages[si][1], stride = kStages[si][2], cin0 = kStages[si][3],
+              cout = kStages[si][4], reps = kStages[si][5];
+    for (int r = 0; r < reps; ++r) {
+      const int ci = r == 0 ? cin0 : cout, ce = ci * exp, sq = std::max(1, ci / 4), s_ = r == 0 ? stride : 1;
+      const std::string bp = p + std::to_string(si + 1) + "." + std::to_string(r) + ".block.";
+      const std::string nm = tag + "mb" + std::to_string(si + 1) + "." + std::to_string(r) + ".";
+      int bi = 0;
+      Tens cur = x;
+      if (exp != 1) {  // 1x1 expand + BN + SiLU -> tcgen05 GEMM
+        const HostTensor* ew = find_w(w, bp + "0.0.weight");
+        if (!ew || !bn_fold(w, bp + "0.1.", ce, s, t)) return VPB_ERR_IO;
+        void* dw_ = e.upload_16(pack_conv(*ew, &s));
+        float* db = e.upload_f32(t);
+        Tens ex = e.act_alloc(x.H, x.W, ce);
+        int rc = e.add_conv(nm + "expand", x, ce, 1, 1, dw_, db, ACT_SILU, VPB_EPI_STORE, &ex, nullptr);
+        if (rc) return rc;
+        cur = ex; bi = 1;
+      }
+      // depthwise + BN + SiLU (+ SE pooling partial sums)
+      const HostTensor* dwt = find_w(w, bp + std::to_string(bi) + ".0.weight");
+      if (!dwt || !bn_fold(w, bp + std::to_string(bi) + ".1.", ce, s, t)) return VPB_ERR_IO;
+      std::vector<float> dwp(static_cast<size_t>(k) * k * ce);
+      for (int c = 0; c < ce; ++c)
+        for (int kk = 0; kk < k * k; ++kk) dwp[static_cast<size_t>(kk) * ce + c] = dwt->f[static_cast<size_t>(c) * k * k + kk] * s[c];
+      float* d_dw = e.upload_f32(dwp);
+      float* d_dwb = e.upload_f32(t);
+      const DwGeom g = dw_geometry(cur.H, cur.W, ce, k, s_);
+      Tens dwo = e.act_alloc(g.Ho, g.Wo, ce);
+      long long* d_part = e.gap_alloc(ce);
+      {
+        const void* in = cur.p; void* o = dwo.p; const int H = cur.H, W = cur.W;
+        e.add_op(nm + "dw", [=](cudaStream_t st) { return vpb_depthwise(dt, in, H, W, ce, k, s_, d_dw, d_dwb, o, d_part, st); },
+                 2.0 * g.Ho * g.Wo * ce * k * k);
+      }
+      // SE gate folded into the projection weights
+      const std::string sp = bp + std::to_string(bi + 1) + ".";
+      const HostTensor *f1 = find_w(w, sp + "fc1.weight"), *b1 = find_w(w, sp + "fc1.bias"),
+                       *f2 = find_w(w, sp + "fc2.weight"), *b2 = find_w(w, sp + "fc2.bias");
+      const HostTensor* pw = find_w(w, bp + std::to_string(bi + 2) + ".0.weight");
+      if (!f1 || !b1 || !f2 || !b2 || !pw || !bn_fold(w, bp + std::to_string(bi + 2) + ".1.", cout, s, t)) return VPB_ERR_IO;
+      float *d_f1 = e.upload_f32(f1->f), *d_b1 = e.upload_f32(b1->f), *d_f2 = e.upload_f32(f2->f), *d_b2 = e.upload_f32(b2->f);
+      std::vector<float> proj(pw->f.size());
+      for (int co = 0; co < cout; ++co)
+        for (int c = 0; c < ce; ++c) proj[static_cast<size_t>(co) * ce + c] = pw->f[static_cast<size_t>(co) * ce + c] * s[co];
+      float* d_proj = e.upload_f32(proj);
+      float* d_pb = e.upload_f32(t);
+      void* d_wscaled = e.dalloc(static_cast<size_t>(cout) * ce * 2, false);
+      {
+        const int HW = g.Ho * g.Wo;
+        e.add_op(nm + "se", [=](cudaStream_t st) {
+          return vpb_se_scale(dt, d_part, HW, ce, sq, d_f1, d_b1, d_f2, d_b2, d_proj, cout, d_wscaled, nullptr, st);
+        }, 2.0 * (2.0 * ce * sq));
+      }
+      // 1x1 project + BN (+ residual; StochasticDepth is identity in eval)
+      const bool residual = (s_ == 1 && ci == cout);
+      Tens po = e.act_alloc(dwo.H, dwo.W, cout);
+      int rc = e.add_conv(nm + "project", dwo, cout, 1, 1, d_wscaled, d_pb, ACT_NONE,
+                          residual ? VPB_EPI_ADD : VPB_EPI_STORE, &po, residual ? &x : nullptr);
+      if (rc) return rc;
+      x = po;
+    }
+    stage_out[si + 1] = x;
+  }
+  // encoder[8]: 1x1 320 -> 1280 + BN + SiLU
+  const HostTensor* hw = find_w(w, p + "8.0.weight");
+  if (!hw || !bn_fold(w, p + "8.1.", 1280, s, t)) return VPB_ERR_IO;
+  void* d_hw = e.upload_16(pack_conv(*hw, &s));
+  float* d_hb = e.upload_f32(t);
+  Tens f4 = e.act_alloc(x.H, x.W, 1280);
+  int rc = e.add_conv(tag + "enc8", x, 1280, 1, 1, d_hw, d_hb, ACT_SILU, VPB_EPI_STORE, &f4, nullptr);
+  if (rc) return rc;
+  out.f[0] = stage_out[0]; out.f[1] = stage_out[2]; out.f[2] = stage_out[3]; out.f[3] = stage_out[4]; out.f[4] = f4;
+  return VPB_OK;
+}
+
+static int conv_layer(vp_engine& e, const WeightMap& w, const std::string& key, const std::string& name,
+                      const Tens& in, int taps, int act, int mode, Tens* out, const Tens* res) {
+  const HostTensor *wt = find_w(w, key + ".weight"), *bt = find_w(w, key + ".bias");
+  if (!wt || !bt) return VPB_ERR_IO;
+  const int Cout = wt->dims[0];
+  if (wt->dims[1] != in.C) { vpb_set_error("%s: Cin %d != input channels %d", key.c_str(), wt->dims[1], in.C); return VPB_ERR_ARG; }
+  void* dw_ = e.upload_16(pack_conv(*wt, nullptr));
+  float* db = e.upload_f32(bt->f);
+  if (!out->p) *out = e.act_alloc(in.H, in.W, (Cout + 7) / 8 * 8);
+  return e.add_conv(name, in, Cout, taps, 1, dw_, db, act, mode, out, res);
+}
+
+// ConvTranspose2d(k2,s2) [+ Conv1x1(skip)] summed before any activation (scene_neck.py:30-32)
+static int up_skip(vp_engine& e, const WeightMap& w, const std::string& p, int i, const std::string& tag,
+                   const Tens& in, const Tens* skip, Tens* out) {
+  const std::string uk = p + "upsample_layer_" + std::to_string(i);
+  const HostTensor *ut = find_w(w, uk + ".weight"), *ub = find_w(w, uk + ".bias");
+  if (!ut || !ub) return VPB_ERR_IO;
+  const int Cout = ut->dims[1];
+  *out = e.act_alloc(in.H * 2, in.W * 2, Cout);
+  if (skip) {
+    int rc = conv_layer(e, w, p + "skip_link_layer_" + std::to_string(i), tag + "skip" + std::to_string(i), *skip, 1,
+                        ACT_NONE, VPB_EPI_STORE, out, nullptr);
+    if (rc) return rc;
+  }
+  void* dw_ = e.upload_16(pack_convT(*ut));
+  float* db = e.upload_f32(ub->f);
+  return e.add_conv(tag + "up" + std::to_string(i), in, Cout, 1, 4, dw_, db, ACT_NONE,
+                    skip ? VPB_EPI_ADD : VPB_EPI_STORE, out, skip ? out : nullptr);
+}
+
+// SceneContext / DepthContext / AutoSteerContext (scene_context.py:25-57)
+static int build_context(vp_engine& e, const WeightMap& w, const std::string& p, const std::string& tag,
+                         const Tens& feat, Tens* ctx) {
+  const int dt = e.dtype, C = feat.C, HW = feat.H * feat.W;
+  float* d_v = static_cast<float*>(e.dalloc(C * 4, false));
+  {
+    const void* in = feat.p;
+    e.add_op(tag + "gap", [=](cudaStream_t st) { return vpb_gap(dt, in, HW, C, C, d_v, st); });
+  }
+  const int dims[4] = {C, 800, 800, 200};
+  const int acts[3] = {ACT_GELU, ACT_GELU, ACT_SIGMOID};
+  float* cur = d_v;
+  for (int i = 0; i < 3; ++i) {
+    const std::string k = p + "context_layer_" + std::to_string(i);
+    const HostTensor *wt = find_w(w, k + ".weight"), *bt = find_w(w, k + ".bias");
+    if (!wt || !bt) return VPB_ERR_IO;
+    float *dw_ = e.upload_f32(wt->f), *db = e.upload_f32(bt->f);
+    float* y = static_cast<float*>(e.dalloc(dims[i + 1] * 4, false));
+    const int in_f = dims[i], out_f = dims[i + 1], a = acts[i];
+    const float* xin = cur;
+    e.add_op(tag + "mlp" + std::to_string(i), [=](cudaStream_t st) { return vpb_linear(xin, dw_, db, in_f, out_f, a, y, st); },
+             2.0 * in_f * out_f);
+    cur = y;
+  }
+  const HostTensor *w3 = find_w(w, p + "context_layer_3.weight"), *b3 = find_w(w, p + "context_layer_3.bias");
+  if (!w3 || !b3) return VPB_ERR_IO;
+  float *d_w3 = e.upload_f32(w3->f), *d_b3 = e.upload_f32(b3->f);
+  Tens c4 = e.act_alloc(feat.H, feat.W, 128);
+  {
+    const float* xin = cur; void* o = c4.p; const int H = feat.H, W = feat.W;
+    e.add_op(tag + "ctx3", [=](cudaStream_t st) { return vpb_ctx_conv1(dt, xin, H, W, d_w3, d_b3, 128, o, st); },
+             2.0 * HW * 128 * 9);
+  }
+  Tens c5, c6;
+  int rc = conv_layer(e, w, p + "context_layer_4", tag + "ctx4", c4, 9, ACT_GELU, VPB_EPI_STORE, &c5, nullptr);
+  if (rc) return rc;
+  rc = conv_layer(e, w, p + "context_layer_5", tag + "ctx5", c5, 9, ACT_GELU, VPB_EPI_STORE, &c6, nullptr);
+  if (rc) return rc;
+  *ctx = e.act_alloc(feat.H, feat.W, C);
+  return conv_layer(e, w, p + "context_layer_6", tag + "ctx6", c6, 9, ACT_GELU, VPB_EPI_MULADD, ctx, &feat);
+}
+
+// SceneNeck / Scene3DNeck / EgoPathNeck (scene_neck.py:26-60)
+static int build_neck(vp_engine& e, const WeightMap& w, const std::string& p, const std::string& tag,
+                      const Tens& ctx, const vp_engine::EncOut& enc, Tens* neck) {
+  Tens d = ctx, u;
+  const int skip_src[3] = {3, 2, 1};
+  for (int b = 0; b < 3; ++b) {
+    int rc = up_skip(e, w, p, b, tag, d, &enc.f[skip_src[b]], &u);
+    if (rc) return rc;
+    Tens a, c;
+    rc = conv_layer(e, w, p + "decode_layer_" + std::to_string(2 * b), tag + "dec" + std::to_string(2 * b), u, 9, ACT_GELU, VPB_EPI_STORE, &a, nullptr);
+    if (rc) return rc;
+    rc = conv_layer(e, w, p + "decode_layer_" + std::to_string(2 * b + 1), tag + "dec" + std::to_string(2 * b + 1), a, 9, ACT_GELU, VPB_EPI_STORE, &c, nullptr);
+    if (rc) return rc;
+    d = c;
+  }
+  *neck = d;
+  return VPB_OK;
+}
+
+static int final_conv(vp_engine& e, const WeightMap& w, const std::string& key, const std::string& name,
+                      const Tens& in, int final_kind, ModelOut& mo) {
+  const HostTensor *wt = find_w(w, key + ".weight"), *bt = find_w(w, key + ".bias");
+  if (!wt || !bt) return VPB_ERR_IO;
+  const int Cout = wt->dims[0];
+  void* dw_ = e.upload_16(pack_conv(*wt, nullptr));
+  float* db = e.upload_f32(bt->f);
+  mo.C = Cout; mo.H = in.H; mo.W = in.W;
+  const size_t n = static_cast<size_t>(Cout) * in.H * in.W;
+  mo.d_raw = static_cast<float*>(e.dalloc(n * 4, false));
+  mo.has_cls = final_kind != VPB_FINAL_NONE;
+  if (mo.has_cls) mo.d_cls = static_cast<uint8_t*>(e.dalloc(static_cast<size_t>(in.H) * in.W, false));
+  void* hp = nullptr;
+  if (cudaMallocHost(&hp, n * 4) != cudaSuccess) { vpb_set_error("cudaMallocHost failed"); return VPB_ERR_CUDA; }
+  e.host_allocs.push_back(hp); mo.h_raw = static_cast<float*>(hp);
+  if (mo.has_cls) {
+    if (cudaMallocHost(&hp, static_cast<size_t>(in.H) * in.W) != cudaSuccess) { vpb_set_error("cudaMallocHost failed"); return VPB_ERR_CUDA; }
+    e.host_allocs.push_back(hp); mo.h_cls = static_cast<uint8_t*>(hp);
+  }
+  return e.add_conv(name, in, Cout, 9, 1, dw_, db, ACT_NONE, VPB_EPI_FINAL, nullptr, nullptr, final_kind, mo.d_raw, mo.d_cls);
+}
+
+// SceneSegHead / Scene3DHead / DomainSegHead (scene_seg_head.py:21-44) and EgoLanesHead
+static int build_head(vp_engine& e, const WeightMap& w, const std::string& p, const std::string& tag, int kind,
+                      const Tens& neck, const vp_engine::EncOut& enc, ModelOut& mo) {
+  int rc;
+  if (kind == VP_EGO_LANES) {  // ego_lanes_head.py:17-26
+    Tens a, b;
+    rc = conv_layer(e, w, p + "decode_layer_6", tag + "dec6", neck, 9, ACT_GELU, VPB_EPI_STORE, &a, nullptr); if (rc) return rc;
+    rc = conv_layer(e, w, p + "decode_layer_7", tag + "dec7", a, 9, ACT_GELU, VPB_EPI_STORE, &b, nullptr); if (rc) return rc;
+    return final_conv(e, w, p + "decode_layer_8", tag + "dec8", b, VPB_FINAL_EGOLANES, mo);
+  }
+  Tens u3, a, b, u4, c, d;
+  rc = up_skip(e, w, p, 3, tag, neck, &enc.f[0], &u3); if (rc) return rc;
+  rc = conv_layer(e, w, p + "decode_layer_6", tag + "dec6", u3, 9, ACT_GELU, VPB_EPI_STORE, &a, nullptr); if (rc) return rc;
+  rc = conv_layer(e, w, p + "decode_layer_7", tag + "dec7", a, 9, ACT_GELU, VPB_EPI_STORE, &b, nullptr); if (rc) return rc;
+  rc = up_skip(e, w, p, 4, tag, b, nullptr, &u4); if (rc) return rc;
+  rc = conv_layer(e, w, p + "decode_layer_8", tag + "dec8", u4, 9, ACT_GELU, VPB_EPI_STORE, &c, nullptr); if (rc) return rc;
+  rc = conv_layer(e, w, p + "decode_layer_9", tag + "dec9", c, 9, ACT_GELU, VPB_EPI_STORE, &d, nullptr); if (rc) return rc;
+  e.taps[tag + "d9"] = d;
+  const int fk = kind == VP_SCENE_SEG ? VPB_FINAL_ARGMAX : kind == VP_DOMAIN_SEG ? VPB_FINAL_THRESH : VPB_FINAL_NONE;
+  return final_conv(e, w, p + "decode_layer_10", tag + "dec10", d, fk, mo);
+}
+
+static int build_model(vp_engine& e, int idx, int kind, const WeightMap& w) {
+  const Prefixes pf = prefixes_for(kind);
+  const std::string tag = std::to_string(idx) + "/";
+  const uint64_t h_enc = hash_prefix(w, pf.enc);
+  vp_engine::EncOut enc;
+  auto ie = e.enc_cache.find(h_enc);
+  if (ie != e.enc_cache.end()) { enc = ie->second; ++e.shared_encoders; }
+  else {
+    int rc = build_encoder(e, w, pf.enc, tag, enc);
+    if (rc) return rc;
+    e.enc_cache[h_enc] = enc;
+  }
+  for (int i = 0; i < 5; ++i) e.taps[tag + "f" + std::to_string(i)] = enc.f[i];
+  uint64_t h_trunk = h_enc;
+  { const uint64_t a = hash_prefix(w, pf.ctx), b = hash_prefix(w, pf.neck); h_trunk = fnv1a(fnv1a(h_trunk, &a, 8), &b, 8); }
+  Tens neck;
+  auto it = e.trunk_cache.find(h_trunk);
+  if (it != e.trunk_cache.end()) { neck = it->second; ++e.shared_trunks; }
+  else {
+    Tens feat = enc.f[4];
+    if (kind == VP_EGO_LANES) {  // BackboneFeatureFusion (backbone_feature_fusion.py:13-38)
+      feat = e.act_alloc(enc.f[4].H, enc.f[4].W, 1456);
+      const int dt = e.dtype; const void *f0 = enc.f[0].p, *f1 = enc.f[1].p, *f2 = enc.f[2].p, *f3 = enc.f[3].p, *f4 = enc.f[4].p;
+      void* o = feat.p; const int H4 = feat.H, W4 = feat.W;
+      e.add_op(tag + "fuse", [=](cudaStream_t st) { return vpb_fuse_pool_concat(dt, f0, f1, f2, f3, f4, H4, W4, o, st); });
+      e.taps[tag + "fused"] = feat;
+    }
+    Tens ctx;
+    int rc = build_context(e, w, pf.ctx, tag, feat, &ctx);
+    if (rc) return rc;
+    e.taps[tag + "context"] = ctx;
+    rc = build_neck(e, w, pf.neck, tag, ctx, enc, &neck);
+    if (rc) return rc;
+    e.trunk_cache[h_trunk] = neck;
+  }
+  e.taps[tag + "neck"] = neck;
+  ModelOut mo; mo.kind = kind;
+  int rc = build_head(e, w, pf.head, tag, kind, neck, enc, mo);
+  if (rc) return rc;
+  e.outs.push_back(mo);
+  return VPB_OK;
+}
+
+static int ensure_frame_buffers(vp_engine& e, size_t bytes) {
+  if (bytes <= e.d_frame_cap) return VPB_OK;
+  if (e.gexec) { cudaGraphExecDestroy(e.gexec); e.gexec = nullptr; }
+  void* p = nullptr;
+  VPB_CUDA_OK(cudaMalloc(&p, bytes + 256));
+  e.dev_allocs.push_back(p);
+  e.d_frame = static_cast<uint8_t*>(p); e.d_frame_cap = bytes;
+  return VPB_OK;
+}
+
+static int launch_all(vp_engine& e, const uint8_t* src_dev, int stride, cudaStream_t st) {
+  if (e.d_gap) VPB_CUDA_OK(cudaMemsetAsync(e.d_gap, 0, e.gap_used * 8, st));
+  int rc = e.pre.launch(src_dev, stride, e.cfg.convention, e.dtype, e.d_pre, e.d_resized, st);
+  if (rc) return rc;
+  for (auto& op : e.ops) { rc = op.launch(st); if (rc) return rc; }
+  return VPB_OK;
+}
+
+// Enqueue one frame's kernels (graph replay when enabled and the geometry is unchanged).
+static int enqueue_frame(vp_engine& e, const uint8_t* src_dev, int h, int w, int stride) {
+  int rc = e.pre.configure(h, w, e.cfg.resize_mode);
+  if (rc) return rc;
+  if (!e.cfg.use_graph) return launch_all(e, src_dev, stride, e.stream);
+  if (!e.gexec || e.g_h != h || e.g_w != w || e.g_stride != stride || e.g_src != src_dev) {
+    if (e.gexec) { cudaGraphExecDestroy(e.gexec); e.gexec = nullptr; }
+    // warm (sets function attributes outside capture), then capture
+    rc = launch_all(e, src_dev, stride, e.stream);
+    if (rc) return rc;
+    VPB_CUDA_OK(cudaStreamSynchronize(e.stream));
+    cudaGraph_t g = nullptr;
+    VPB_CUDA_OK(cudaStreamBeginCapture(e.stream, cudaStreamCaptureModeThreadLocal));
+    rc = launch_all(e, src_dev, stride, e.stream);
+    cudaError_t ce = cudaStreamEndCapture(e.stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) { vpb_set_error("graph capture failed: %s", cudaGetErrorString(ce)); return VPB_ERR_CUDA; }
+    ce = cudaGraphInstantiate(&e.gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) { vpb_set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); return VPB_ERR_CUDA; }
+    e.g_h = h; e.g_w = w; e.g_stride = stride; e.g_src = src_dev;
+  }
+  VPB_CUDA_OK(cudaGraphLaunch(e.gexec, e.stream));
+  return VPB_OK;
+}
+
+}  // namespace vpb
+
+// ====================================================================== C-ABI
+extern "C" const char* vp_last_error(void) { return vpb_last_error(); }
+
+extern "C" int vp_engine_create(const vp_engine_config* cfg, vp_engine** out) {
+  if (!cfg || !out || cfg->n_models < 1 || cfg->n_models > VP_MAX_MODELS) {
+    vpb_set_error("vp_engine_create: bad config");
+    return VPB_ERR_ARG;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    vpb_set_error("vp_engine_create: no CUDA device (this engine has no CPU fallback)");
+    return VPB_ERR_CUDA;
+  }
+  VPB_CUDA_OK(cudaSetDevice(cfg->gpu_id));
+  cudaDeviceProp prop;
+  VPB_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->gpu_id));
+  if (prop.major != 10) {
+    vpb_set_error("vp_engine_create: device %d is sm_%d%d; this library is built for sm_100a only", cfg->gpu_id, prop.major, prop.minor);
+    return VPB_ERR_CUDA;
+  }
+  std::unique_ptr<vp_engine> e(new vp_engine());
+  e->cfg = *cfg;
+  e->dtype = cfg->dtype == VPB_BF16 ? VPB_BF16 : VPB_F16;
+  if (cfg->stream) e->stream = static_cast<cudaStream_t>(cfg->stream);
+  else { VPB_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
+  e->d_pre = e->dalloc(static_cast<size_t>(kNetH) * kNetW * 4 * 2, false);
+  e->d_resized = static_cast<uint8_t*>(e->dalloc(static_cast<size_t>(kNetH) * kNetW * 3, false));
+  {
+    Tens pre; pre.p = e->d_pre; pre.H = kNetH; pre.W = kNetW; pre.C = 4;
+    e->taps["pre"] = pre;
+  }
+  for (int i = 0; i < cfg->n_models; ++i) {
+    if (!cfg->weights[i] || !cfg->weights[i][0]) {
+      // same condition the reference rejects: scene_seg_infer.py:32-33
+      vpb_set_error("No path to checkpoint file provided for model %d", i);
+      return VPB_ERR_ARG;
+    }
+    WeightMap w;
+    int rc = load_vpw(cfg->weights[i], w);
+    if (rc) return rc;
+    rc = build_model(*e, i, cfg->kinds[i], w);
+    if (rc) return rc;
+  }
+  VPB_CUDA_OK(cudaDeviceSynchronize());
+  *out = e.release();
+  return VPB_OK;
+}
+
+extern "C" void vp_engine_destroy(vp_engine* e) { delete e; }
+
+extern "C" int vp_engine_num_models(const vp_engine* e) { return e ? static_cast<int>(e->outs.size()) : 0; }
+
+extern "C" uint8_t* vp_engine_pinned_frame(vp_engine* e, size_t bytes) {
+  if (!e) return nullptr;
+  if (bytes > e->h_frame_cap) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { vpb_set_error("cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    e->host_allocs.push_back(p);
+    e->h_frame = static_cast<uint8_t*>(p); e->h_frame_cap = bytes;
+  }
+  return e->h_frame;
+}
+
+extern "C" int vp_engine_infer_device(vp_engine* e, const uint8_t* frame_dev, int h, int w, int stride) {
+  if (!e || !frame_dev || h <= 0 || w <= 0 || stride < w * 3) { vpb_set_error("vp_engine_infer_device: bad arguments"); return VPB_ERR_ARG; }
+  return enqueue_frame(*e, frame_dev, h, w, stride);
+}
+
+extern "C" int vp_engine_sync(vp_engine* e) {
+  if (!e) return VPB_ERR_ARG;
+  VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return VPB_OK;
+}
+
+extern "C" int vp_engine_infer(vp_engine* e, const uint8_t* frame_host, int h, int w, int stride) {
+  if (!e || !frame_host || h <= 0 || w <= 0 || stride < w * 3) { vpb_set_error("vp_engine_infer: bad arguments"); return VPB_ERR_ARG; }
+  const size_t bytes = static_cast<size_t>(h) * stride;
+  int rc = ensure_frame_buffers(*e, bytes);
+  if (rc) return rc;
+  VPB_CUDA_OK(cudaMemcpyAsync(e->d_frame, frame_host, bytes, cudaMemcpyHostToDevice, e->stream));
+  rc = enqueue_frame(*e, e->d_frame, h, w, stride);
+  if (rc) return rc;
+  for (auto& mo : e->outs) {
+    if (mo.has_cls)
+      VPB_CUDA_OK(cudaMemcpyAsync(mo.h_cls, mo.d_cls, static_cast<size_t>(mo.H) * mo.W, cudaMemcpyDeviceToHost, e->stream));
+    if (e->cfg.fetch_raw || !mo.has_cls || mo.kind == VP_EGO_LANES)
+      VPB_CUDA_OK(cudaMemcpyAsync(mo.h_raw, mo.d_raw, static_cast<size_t>(mo.C) * mo.H * mo.W * 4, cudaMemcpyDeviceToHost, e->stream));
+  }
+  VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return VPB_OK;
+}
+
+extern "C" int vp_engine_fetch_raw(vp_engine* e, int idx) {
+  if (!e || idx < 0 || idx >= static_cast<int>(e->outs.size())) return VPB_ERR_ARG;
+  auto& mo = e->outs[idx];
+  VPB_CUDA_OK(cudaMemcpyAsync(mo.h_raw, mo.d_raw, static_cast<size_t>(mo.C) * mo.H * mo.W * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (mo.has_cls)
+    VPB_CUDA_OK(cudaMemcpyAsync(mo.h_cls, mo.d_cls, static_cast<size_t>(mo.H) * mo.W, cudaMemcpyDeviceToHost, e->stream));
+  VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return VPB_OK;
+}
+
+extern "C" int vp_engine_output(vp_engine* e, int idx, vp_output* o) {
+  if (!e || !o || idx < 0 || idx >= static_cast<int>(e->outs.size())) { vpb_set_error("vp_engine_output: bad index"); return VPB_ERR_ARG; }
+  const auto& mo = e->outs[idx];
+  o->kind = mo.kind; o->channels = mo.C; o->height = mo.H; o->width = mo.W;
+  o->raw_host = mo.h_raw; o->cls_host = mo.has_cls ? mo.h_cls : nullptr;
+  o->raw_dev = mo.d_raw; o->cls_dev = mo.has_cls ? mo.d_cls : nullptr;
+  return VPB_OK;
+}
+
+extern "C" int vp_engine_get_stats(const vp_engine* e, vp_engine_stats* s) {
+  if (!e || !s) return VPB_ERR_ARG;
+  memset(s, 0, sizeof(*s));
+  s->n_launches = static_cast<int>(e->ops.size()) + 1;
+  for (const auto& op : e->ops) {
+    s->total_flops += op.flops;
+    if (op.gemm) { ++s->n_gemm_launches; s->gemm_flops += op.flops; }
+  }
+  s->weight_bytes = e->weight_bytes; s->act_bytes = e->act_bytes;
+  s->shared_encoders = e->shared_encoders; s->shared_trunks = e->shared_trunks;
+  return VPB_OK;
+}
+
+extern "C" int vp_engine_profile(vp_engine* e, int max_ops, float* ms, double* flops, const char** names, int* is_gemm, int* n_ops) {
+  if (!e || !ms || !n_ops) return VPB_ERR_ARG;
+  if (!e->g_src) { vpb_set_error("vp_engine_profile: run one inference first"); return VPB_ERR_STATE; }
+  const int n = static_cast<int>(e->ops.size()) + 1;
+  *n_ops = n;
+  if (n > max_ops) { vpb_set_error("vp_engine_profile: need room for %d ops", n); return VPB_ERR_ARG; }
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& x : ev) VPB_CUDA_OK(cudaEventCreate(&x));
+  if (e->d_gap) VPB_CUDA_OK(cudaMemsetAsync(e->d_gap, 0, e->gap_used * 8, e->stream));
+  VPB_CUDA_OK(cudaEventRecord(ev[0], e->stream));
+  int rc = e->pre.launch(e->g_src, e->g_stride, e->cfg.convention, e->dtype, e->d_pre, e->d_resized, e->stream);
+  if (rc) return rc;
+  VPB_CUDA_OK(cudaEventRecord(ev[1], e->stream));
+  for (int i = 0; i < n - 1; ++i) {
+    rc = e->ops[i].launch(e->stream);
+    if (rc) return rc;
+    VPB_CUDA_OK(cudaEventRecord(ev[i + 2], e->stream));
+  }
+  VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
+  static const char* kPre = "preprocess";
+  for (int i = 0; i < n; ++i) {
+    VPB_CUDA_OK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    if (flops) flops[i] = i == 0 ? 0.0 : e->ops[i - 1].flops;
+    if (names) names[i] = i == 0 ? kPre : e->ops[i - 1].name.c_str();
+    if (is_gemm) is_gemm[i] = i == 0 ? 0 : (e->ops[i - 1].gemm ? 1 : 0);
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  return VPB_OK;
+}
+
+extern "C" int vp_engine_read_resized(vp_engine* e, uint8_t* dst) {
+  if (!e || !dst) return VPB_ERR_ARG;
+  VPB_CUDA_OK(cudaMemcpyAsync(dst, e->d_resized, static_cast<size_t>(kNetH) * kNetW * 3, cudaMemcpyDeviceToHost, e->stream));
+  VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return VPB_OK;
+}
+
+namespace vpb {
+template <class T> __global__ void tap_to_f32_nchw(const T* in, int H, int W, int C, int Cvalid, float* out) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(H) * W * Cvalid) return;
+  const int c = static_cast<int>(i / (static_cast<long>(H) * W));
+  const long pix = i - static_cast<long>(c) * H * W;
+  out[i] = static_cast<float>(in[pix * C + c]);
+}
+}  // namespace vpb
+
+extern "C" long vp_engine_read_tap(vp_engine* e, const char* name, float* dst, long cap, int* c, int* h, int* w) {
+  if (!e || !name) return VPB_ERR_ARG;
+  auto it = e->taps.find(name);
+  if (it == e->taps.end()) { vpb_set_error("no tap '%s'", name); return VPB_ERR_ARG; }
+  const Tens& a = it->second;
+  const int Cv = (strcmp(name, "pre") == 0) ? 3 : a.C;
+  const long n = static_cast<long>(a.H) * a.W * Cv;
+  if (c) *c = Cv; if (h) *h = a.H; if (w) *w = a.W;
+  if (!dst) return n;
+  if (cap < n) { vpb_set_error("tap buffer too small"); return VPB_ERR_ARG; }
+  float* d = nullptr;
+  VPB_CUDA_OK(cudaMalloc(&d, n * 4));
+  const int blocks = static_cast<int>((n + 255) / 256);
+  if (e->dtype == VPB_BF16) tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __nv_bfloat16*>(a.p), a.H, a.W, a.C, Cv, d);
+  else tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __half*>(a.p), a.H, a.W, a.C, Cv, d);
+  cudaError_t ce = cudaMemcpyAsync(dst, d, n * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  if (ce != cudaSuccess) { vpb_set_error("read_tap: %s", cudaGetErrorString(ce)); return VPB_ERR_CUDA; }
+  return n;
+}

@@ -1,0 +1,36 @@
+// ops_internal.h — C++-side declarations shared between the kernels' launchers and the engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "../../include/vp_b200_ops.h"
+
+namespace vpb {
+
+static constexpr int kNetH = 320, kNetW = 640;  // the only network input size (scene_seg_infer.py:40-42)
+
+void resize_tables_host(int mode, int in_size, int out_size, std::vector<int>& bounds,
+                        std::vector<int>& coeffs, int& ksize);
+
+// Pre-process plan: coefficient tables resident on the device for one (input size, mode).
+struct PreprocessPlan {
+  int h = 0, w = 0, mode = -1;
+  int OH = kNetH, OW = kNetW;
+  int xks = 0, yks = 0;
+  int rows_cap = 0, patch_w_cap = 0;
+  size_t smem_bytes = 0;
+  int* d_tables = nullptr;
+  size_t off_xb = 0, off_xk = 0, off_yb = 0, off_yk = 0;
+  int configure(int in_h, int in_w, int mode);
+  int launch(const uint8_t* src, int stride, int convention, int dtype, void* out, uint8_t* out_u8,
+             cudaStream_t stream) const;
+  ~PreprocessPlan();
+};
+
+// depthwise launch geometry (shared by the op entry point and the engine's buffer sizing)
+struct DwGeom {
+  int Ho, Wo, G, PPB, threads, pix_per_block, nblocks;
+};
+DwGeom dw_geometry(int H, int W, int C, int k, int stride);
+
+}  // namespace vpb

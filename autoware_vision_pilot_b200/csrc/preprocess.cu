@@ -1,0 +1,336 @@
+// preprocess.cu — fused resize + /255 + normalise + HWC uint8 -> NHWC(4) 16-bit, one kernel.
+//
+// Replaces the caller-side resize plus the helper's tensor conversion (reference):
+//   P0a  PIL  image.resize((640,320))  (BICUBIC, antialias)  Models/visualizations/SceneSeg/image_visualization.py:108-109
+//   P0b  cv::resize INTER_LINEAR on BGR, BGR-ordered stats   VisionPilot/middleware_recipes/common/backends/tensorrt_backend.cpp:160-177
+//   P0c  cv::resize INTER_LINEAR + BGR->RGB                  VisionPilot/production_release/src/inference/tensorrt_engine.cpp:190-220
+//   P1   ToTensor + Normalize                                Models/inference/scene_seg_infer.py:15-20,44-45
+//
+// The uint8 resize stage is integer arithmetic and is reproduced bit-exactly:
+//  * Pillow: separable, horizontal pass first, coefficients normalised in double and quantised to
+//    22-bit fixed point, uint8 clip after EACH pass (the intermediate rounding is kept: the
+//    horizontal result is staged as uint8 in shared memory before the vertical pass);
+//  * OpenCV: 11-bit weights, (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.
+// Coefficient tables are computed on the host in double (resize_tables_build), exactly the
+// libraries' formulas, and uploaded once per (input size, mode).
+//
+// Output: [320][640][4] fp16/bf16, channel 3 = 0 — the 8-byte pixel the stem conv reads with
+// one load.  Optionally also the resized uint8 image (tests compare it bit-exact).
+#include "common.cuh"
+#include "ops_internal.h"
+#include <cmath>
+#include <vector>
+
+namespace vpb {
+
+// ---------------------------------------------------------------- host: coefficient tables
+static double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc (BICUBIC, support 2.0).
+static void pil_axis(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& coeffs,
+                     int& ksize) {
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  bounds.assign(out_size, 0);
+  coeffs.assign(static_cast<size_t>(out_size) * ksize, 0);
+  std::vector<double> k(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    const double ss = 1.0 / filterscale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = bicubic_filter((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    bounds[xx] = xmin;
+    for (int x = 0; x < xmax; ++x) {
+      const double v = k[x];
+      coeffs[static_cast<size_t>(xx) * ksize + x] =
+          v < 0 ? static_cast<int>(-0.5 + v * (1 << 22)) : static_cast<int>(0.5 + v * (1 << 22));
+    }
+  }
+}
+
+// OpenCV resize.cpp (INTER_LINEAR, 8u): index + two 11-bit weights per output coordinate.
+static void cv_axis(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& coeffs,
+                    int& ksize) {
+  ksize = 2;
+  bounds.assign(out_size, 0);
+  coeffs.assign(static_cast<size_t>(out_size) * 2, 0);
+  const double scale = static_cast<double>(in_size) / out_size;
+  for (int d = 0; d < out_size; ++d) {
+    float fx = static_cast<float>((d + 0.5) * scale - 0.5);
+    int sx = static_cast<int>(std::floor(fx));
+    fx -= sx;
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= in_size - 1) { sx = in_size - 1; fx = 0.f; }
+    bounds[d] = sx;
+    coeffs[2 * d + 0] = static_cast<int>(std::nearbyint((1.f - fx) * 2048.f));
+    coeffs[2 * d + 1] = static_cast<int>(std::nearbyint(fx * 2048.f));
+  }
+}
+
+void resize_tables_host(int mode, int in_size, int out_size, std::vector<int>& bounds,
+                        std::vector<int>& coeffs, int& ksize) {
+  if (mode == VPB_RESIZE_PIL_BICUBIC) pil_axis(in_size, out_size, bounds, coeffs, ksize);
+  else cv_axis(in_size, out_size, bounds, coeffs, ksize);
+}
+
+// ---------------------------------------------------------------- device
+struct PreParams {
+  const uint8_t* src;   // [h][stride] bytes, 3 interleaved channels
+  int h, w, stride;
+  int mode;             // VPB_RESIZE_*
+  int swap_rb;          // 1: tensor channel c = source channel 2-c
+  int mul_inv255;       // 1: x * (1/255) (OpenCV convertTo), 0: x / 255 (ToTensor)
+  float mean[3], stdv[3];
+  const int* xb; const int* xk; int xks;   // horizontal bounds / coeffs / ksize
+  const int* yb; const int* yk; int yks;   // vertical
+  void* out;            // [OH][OW][4] 16-bit
+  uint8_t* out_u8;      // optional [OH][OW][3] resized image in tensor channel order
+  int OH, OW;
+};
+
+template <class E>
+__device__ __forceinline__ void emit_pixel(const PreParams& p, int oy, int ox, const int (&u)[3]) {
+  float v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int s = p.swap_rb ? u[2 - c] : u[c];
+    float x = static_cast<float>(s);
+    x = p.mul_inv255 ? x * (1.0f / 255.0f) : __fdiv_rn(x, 255.0f);
+    v[c] = __fdiv_rn(x - p.mean[c], p.stdv[c]);
+    if (p.out_u8) p.out_u8[(static_cast<size_t>(oy) * p.OW + ox) * 3 + c] = static_cast<uint8_t>(s);
+  }
+  uint2 o;
+  o.x = pack2<E>(v[0], v[1]);
+  o.y = pack2<E>(v[2], 0.f);
+  reinterpret_cast<uint2*>(p.out)[static_cast<size_t>(oy) * p.OW + ox] = o;
+}
+
+static constexpr int kTX = 32, kTY = 8;       // output tile per block
+static constexpr int kMaxRows = 72;           // input rows one tile may need (checked on host)
+static constexpr int kMaxPatchBytes = 20480;  // staged input patch bytes per block (checked on host)
+
+// Pillow path: stage input patch -> horizontal pass to uint8 smem -> vertical pass -> normalise.
+template <class E>
+__global__ void __launch_bounds__(256) preprocess_pil_kernel(const PreParams p, int rows_cap,
+                                                              int patch_w_cap) {
+  extern __shared__ uint8_t sm[];
+  uint8_t* patch = sm;                                              // [rows][patch_w*3]
+  uint8_t* inter = sm + static_cast<size_t>(rows_cap) * patch_w_cap * 3;  // [rows][kTX][3]
+  const int ox0 = blockIdx.x * kTX, oy0 = blockIdx.y * kTY;
+  const int ox1 = min(ox0 + kTX, p.OW) - 1, oy1 = min(oy0 + kTY, p.OH) - 1;
+  // input extents of this tile (bounds are monotone non-decreasing)
+  const int x_lo = p.xb[ox0];
+  int x_hi = 0;
+  for (int x = ox0; x <= ox1; ++x) x_hi = max(x_hi, min(p.xb[x] + p.xks, p.w));
+  const int y_lo = p.yb[oy0];
+  int y_hi = 0;
+  for (int y = oy0; y <= oy1; ++y) y_hi = max(y_hi, min(p.yb[y] + p.yks, p.h));
+  const int rows = y_hi - y_lo, pw = x_hi - x_lo, pwb = pw * 3;
+
+  for (int i = threadIdx.x; i < rows * pwb; i += blockDim.x) {
+    const int r = i / pwb, b = i - r * pwb;
+    patch[r * patch_w_cap * 3 + b] = __ldg(p.src + static_cast<size_t>(y_lo + r) * p.stride + x_lo * 3 + b);
+  }
+  __syncthreads();
+  // horizontal pass
+  const int ncols = ox1 - ox0 + 1;
+  for (int i = threadIdx.x; i < rows * ncols * 3; i += blockDim.x) {
+    const int c = i % 3;
+    const int xo = (i / 3) % ncols;
+    const int r = i / (3 * ncols);
+    const int ox = ox0 + xo;
+    const int xb = p.xb[ox];
+    const int n = min(p.xks, p.w - xb);
+    const int* k = p.xk + static_cast<size_t>(ox) * p.xks;
+    const uint8_t* row = patch + r * patch_w_cap * 3 + (xb - x_lo) * 3 + c;
+    int acc = 1 << 21;
+    for (int t = 0; t < n; ++t) acc += k[t] * static_cast<int>(row[3 * t]);
+    acc >>= 22;
+    inter[(r * kTX + xo) * 3 + c] = static_cast<uint8_t>(min(max(acc, 0), 255));
+  }
+  __syncthreads();
+  // vertical pass + normalise: one thread per output pixel
+  for (int i = threadIdx.x; i < kTX * kTY; i += blockDim.x) {
+    const int xo = i % kTX, yo = i / kTX;
+    const int ox = ox0 + xo, oy = oy0 + yo;
+    if (ox >= p.OW || oy >= p.OH) continue;
+    const int yb = p.yb[oy];
+    const int n = min(p.yks, p.h - yb);
+    const int* k = p.yk + static_cast<size_t>(oy) * p.yks;
+    int u[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int acc = 1 << 21;
+      for (int t = 0; t < n; ++t) acc += k[t] * static_cast<int>(inter[((yb - y_lo + t) * kTX + xo) * 3 + c]);
+      acc >>= 22;
+      u[c] = min(max(acc, 0), 255);
+    }
+    emit_pixel<E>(p, oy, ox, u);
+  }
+}
+
+// OpenCV path (and the no-resize path): one thread per output pixel, gather from global.
+template <class E>
+__global__ void __launch_bounds__(256) preprocess_direct_kernel(const PreParams p) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  if (ox >= p.OW) return;
+  int u[3];
+  if (p.mode == VPB_RESIZE_NONE) {
+    const uint8_t* s = p.src + static_cast<size_t>(oy) * p.stride + ox * 3;
+    u[0] = s[0]; u[1] = s[1]; u[2] = s[2];
+  } else {
+    const int sx = p.xb[ox], sy = p.yb[oy];
+    const int sx1 = min(sx + 1, p.w - 1), sy1 = min(sy + 1, p.h - 1);
+    const int a0 = p.xk[2 * ox], a1 = p.xk[2 * ox + 1];
+    const int b0 = p.yk[2 * oy], b1 = p.yk[2 * oy + 1];
+    const uint8_t* r0 = p.src + static_cast<size_t>(sy) * p.stride;
+    const uint8_t* r1 = p.src + static_cast<size_t>(sy1) * p.stride;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
+      const int h1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+      u[c] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    }
+  }
+  emit_pixel<E>(p, oy, ox, u);
+}
+
+// ---------------------------------------------------------------- host: plan
+int PreprocessPlan::configure(int in_h, int in_w, int mode_) {
+  if (in_h == h && in_w == w && mode_ == mode && d_tables) return VPB_OK;
+  if (mode_ == VPB_RESIZE_NONE && (in_h != OH || in_w != OW)) {
+    vpb_set_error("preprocess: resize mode 'none' needs a %dx%d input, got %dx%d", OW, OH, in_w, in_h);
+    return VPB_ERR_ARG;
+  }
+  h = in_h; w = in_w; mode = mode_;
+  std::vector<int> xb, xk, yb, yk;
+  if (mode == VPB_RESIZE_NONE) {
+    xks = yks = 0;
+    xb.assign(OW, 0); yb.assign(OH, 0); xk.assign(1, 0); yk.assign(1, 0);
+  } else {
+    resize_tables_host(mode, w, OW, xb, xk, xks);
+    resize_tables_host(mode, h, OH, yb, yk, yks);
+  }
+  if (mode == VPB_RESIZE_PIL_BICUBIC) {
+    // worst-case tile extents for the shared-memory staging
+    rows_cap = 0; patch_w_cap = 0;
+    for (int y0 = 0; y0 < OH; y0 += kTY) {
+      int hi = 0;
+      for (int y = y0; y < std::min(y0 + kTY, OH); ++y) hi = std::max(hi, std::min(yb[y] + yks, h));
+      rows_cap = std::max(rows_cap, hi - yb[y0]);
+    }
+    for (int x0 = 0; x0 < OW; x0 += kTX) {
+      int hi = 0;
+      for (int x = x0; x < std::min(x0 + kTX, OW); ++x) hi = std::max(hi, std::min(xb[x] + xks, w));
+      patch_w_cap = std::max(patch_w_cap, hi - xb[x0]);
+    }
+    smem_bytes = static_cast<size_t>(rows_cap) * patch_w_cap * 3 + static_cast<size_t>(rows_cap) * kTX * 3;
+    if (smem_bytes > 200 * 1024) {
+      vpb_set_error("preprocess: %dx%d -> %dx%d needs %zu B of shared memory per tile (input too large)",
+                    w, h, OW, OH, smem_bytes);
+      return VPB_ERR_ARG;
+    }
+  }
+  const size_t n = xb.size() + xk.size() + yb.size() + yk.size();
+  if (d_tables) cudaFree(d_tables);
+  VPB_CUDA_OK(cudaMalloc(&d_tables, n * sizeof(int)));
+  std::vector<int> all;
+  all.reserve(n);
+  off_xb = 0; all.insert(all.end(), xb.begin(), xb.end());
+  off_xk = all.size(); all.insert(all.end(), xk.begin(), xk.end());
+  off_yb = all.size(); all.insert(all.end(), yb.begin(), yb.end());
+  off_yk = all.size(); all.insert(all.end(), yk.begin(), yk.end());
+  VPB_CUDA_OK(cudaMemcpy(d_tables, all.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  return VPB_OK;
+}
+
+PreprocessPlan::~PreprocessPlan() {
+  if (d_tables) cudaFree(d_tables);
+}
+
+int PreprocessPlan::launch(const uint8_t* src, int stride, int convention, int dtype, void* out,
+                           uint8_t* out_u8, cudaStream_t stream) const {
+  PreParams p;
+  p.src = src; p.h = h; p.w = w; p.stride = stride; p.mode = mode;
+  // conventions: see include/vp_b200_ops.h
+  static const float kMeanRGB[3] = {0.485f, 0.456f, 0.406f}, kStdRGB[3] = {0.229f, 0.224f, 0.225f};
+  p.swap_rb = convention == VPB_CONV_BGR_SWAP ? 1 : 0;
+  p.mul_inv255 = convention == VPB_CONV_RGB ? 0 : 1;
+  for (int c = 0; c < 3; ++c) {
+    const int s = convention == VPB_CONV_BGR_NOSWAP ? 2 - c : c;   // BGR-ordered stats (tensorrt_backend.cpp:167-168)
+    p.mean[c] = kMeanRGB[s];
+    p.stdv[c] = kStdRGB[s];
+  }
+  p.xb = d_tables + off_xb; p.xk = d_tables + off_xk; p.xks = xks;
+  p.yb = d_tables + off_yb; p.yk = d_tables + off_yk; p.yks = yks;
+  p.out = out; p.out_u8 = out_u8; p.OH = OH; p.OW = OW;
+  if (mode == VPB_RESIZE_PIL_BICUBIC) {
+    dim3 grid((OW + kTX - 1) / kTX, (OH + kTY - 1) / kTY);
+    if (dtype == VPB_BF16) {
+      VPB_CUDA_OK(cudaFuncSetAttribute(preprocess_pil_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      preprocess_pil_kernel<BF16><<<grid, 256, smem_bytes, stream>>>(p, rows_cap, patch_w_cap);
+    } else {
+      VPB_CUDA_OK(cudaFuncSetAttribute(preprocess_pil_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      preprocess_pil_kernel<F16><<<grid, 256, smem_bytes, stream>>>(p, rows_cap, patch_w_cap);
+    }
+  } else {
+    dim3 grid((OW + 255) / 256, OH);
+    if (dtype == VPB_BF16) preprocess_direct_kernel<BF16><<<grid, 256, 0, stream>>>(p);
+    else preprocess_direct_kernel<F16><<<grid, 256, 0, stream>>>(p);
+  }
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}
+
+}  // namespace vpb
+
+// ---------------------------------------------------------------- C-ABI
+extern "C" int vpb_resize_tables_host(int mode, int in_size, int out_size, int* bounds, int* coeffs,
+                                      int coeffs_cap, int* ksize) {
+  if (!bounds || !coeffs || !ksize || in_size <= 0 || out_size <= 0 ||
+      (mode != VPB_RESIZE_PIL_BICUBIC && mode != VPB_RESIZE_CV_LINEAR)) {
+    vpb_set_error("vpb_resize_tables_host: bad arguments");
+    return VPB_ERR_ARG;
+  }
+  std::vector<int> b, k;
+  int ks = 0;
+  vpb::resize_tables_host(mode, in_size, out_size, b, k, ks);
+  if (static_cast<int>(k.size()) > coeffs_cap) {
+    vpb_set_error("vpb_resize_tables_host: coeffs_cap %d < %zu", coeffs_cap, k.size());
+    return VPB_ERR_ARG;
+  }
+  for (int i = 0; i < out_size; ++i) bounds[i] = b[i];
+  for (size_t i = 0; i < k.size(); ++i) coeffs[i] = k[i];
+  *ksize = ks;
+  return VPB_OK;
+}
+
+extern "C" int vpb_preprocess(const uint8_t* src_dev, int h, int w, int stride, int resize_mode,
+                              int convention, int dtype, void* out_dev, uint8_t* out_u8_dev,
+                              void* stream) {
+  static thread_local vpb::PreprocessPlan plan;
+  int rc = plan.configure(h, w, resize_mode);
+  if (rc != VPB_OK) return rc;
+  return plan.launch(src_dev, stride, convention, dtype, out_dev, out_u8_dev,
+                     static_cast<cudaStream_t>(stream));
+}

@@ -71,6 +71,62 @@ typedef struct {
 } vpb_conv_args;
 int vpb_conv_gemm(const vpb_conv_args* a, void* stream);
 
+/* ---- fused pre-process (resize + /255 + normalise + HWC uint8 -> [320][640][4] 16-bit) ----
+ * resize_mode: how the caller's frame is brought to 640x320
+ *   NONE        frame already 640x320 (Models/inference/scene_seg_infer.py:40-42)
+ *   PIL_BICUBIC Pillow Image.resize default (Models/visualizations/SceneSeg/image_visualization.py:108-109)
+ *   CV_LINEAR   cv::resize INTER_LINEAR (tensorrt_backend.cpp:163, tensorrt_engine.cpp:194-195)
+ * convention: channel order / normalisation arithmetic of the boundary being replaced
+ *   RGB         Python helpers: RGB in, x/255 then (x-mean)/std            (scene_seg_infer.py:15-20)
+ *   BGR_NOSWAP  generic C++ backend: BGR in, no swap, BGR-ordered stats,
+ *               x*(1/255)                                                  (tensorrt_backend.cpp:160-177)
+ *   BGR_SWAP    EgoLanes C++ engine: BGR in -> RGB, RGB stats, x*(1/255)   (tensorrt_engine.cpp:190-220)
+ * out_u8 (optional): the resized uint8 image [320][640][3] in tensor channel order. */
+enum { VPB_RESIZE_NONE = 0, VPB_RESIZE_PIL_BICUBIC = 1, VPB_RESIZE_CV_LINEAR = 2 };
+enum { VPB_CONV_RGB = 0, VPB_CONV_BGR_NOSWAP = 1, VPB_CONV_BGR_SWAP = 2 };
+int vpb_preprocess(const uint8_t* src_dev, int h, int w, int stride, int resize_mode, int convention,
+                   int dtype, void* out_dev, uint8_t* out_u8_dev, void* stream);
+/* Host-only: the integer coefficient tables the kernel uses (bounds[out_size],
+ * coeffs[out_size*ksize]); lets a CPU test pin them against Pillow / OpenCV without a GPU. */
+int vpb_resize_tables_host(int mode, int in_size, int out_size, int* bounds, int* coeffs,
+                           int coeffs_cap, int* ksize);
+
+/* ---- EfficientNet-B0 encoder pieces (torchvision efficientnet_b0().features, reached through
+ *      Models/model_components/backbone.py:9-22; BatchNorm folded at load) ---- */
+/* stem: Conv3x3 s2 p1 (3->32) + BN + SiLU.  in [H][W][4] 16-bit -> out [H/2][W/2][32].
+ * w: fp32 [27][32] (tap-major ky,kx,c), bias fp32 [32]. */
+int vpb_stem_conv(int dtype, const void* in, int H, int W, const float* w, const float* bias,
+                  void* out, void* stream);
+/* depthwise k x k (k = 3 or 5), stride 1 or 2, pad (k-1)/2, + bias + SiLU; also accumulates the
+ * squeeze-excitation average pool: gap_acc[C] int64, 2^-24 fixed point, must be zero on entry
+ * (integer atomics => the pooled sum is bit-reproducible regardless of block order).
+ * in [H][W][C] -> out [Ho][Wo][C]; w fp32 [k*k][C]. */
+int vpb_depthwise(int dtype, const void* in, int H, int W, int C, int k, int stride, const float* w,
+                  const float* bias, void* out, long long* gap_acc, void* stream);
+/* squeeze-excitation: mean = gap_acc * 2^-24 / HW; s = sigmoid(W2 silu(W1 mean + b1) + b2); then
+ * w_scaled[n][k] = w_proj[n][k] * s[k]  (the channel scale is folded into the following 1x1
+ * projection's weights instead of re-writing the activation tensor).
+ * w1 fp32 [sq][C], w2 fp32 [C][sq], w_proj fp32 [Cout][C] -> w_scaled 16-bit [Cout][C];
+ * scale_out (optional) fp32 [C]. */
+int vpb_se_scale(int dtype, const long long* gap_acc, int HW, int C, int sq, const float* w1,
+                 const float* b1, const float* w2, const float* b2, const float* w_proj, int Cout,
+                 void* w_scaled, float* scale_out, void* stream);
+
+/* ---- context block pieces (scene_context.py:25-57 / auto_steer_context.py:28-60) ---- */
+/* global average pool over [HW][C] 16-bit -> fp32 [C] (scene_context.py:27) */
+int vpb_gap(int dtype, const void* in, int HW, int C, int ld, float* out, void* stream);
+/* y = act(W x + b), fp32, W [out][in] (scene_context.py:30-38) */
+int vpb_linear(const float* x, const float* w, const float* b, int in_f, int out_f, int act, float* y,
+               void* stream);
+/* context_layer_3: Conv3x3 1->128 + GELU on the 10x20 map (scene_context.py:41-47).
+ * in fp32 [H][W], w fp32 [Cout][9], out [H][W][Cout] 16-bit */
+int vpb_ctx_conv1(int dtype, const float* in, int H, int W, const float* w, const float* b, int Cout,
+                  void* out, void* stream);
+/* BackboneFeatureFusion (backbone_feature_fusion.py:13-38): 4/3/2/1 x MaxPool2x2 of f0..f3,
+ * concatenated with f4 -> [H4][W4][32+24+40+80+1280]. */
+int vpb_fuse_pool_concat(int dtype, const void* f0, const void* f1, const void* f2, const void* f3,
+                         const void* f4, int H4, int W4, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

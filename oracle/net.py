@@ -259,3 +259,53 @@ def postprocess(model: str, out: torch.Tensor):
         o[o <= 0] = 0.0
         o[o > 0] = 1.0
     return o
+
+
+def preprocess_cpp_generic(bgr_u8_hwc, resize_fn) -> torch.Tensor:
+    """TensorRTBackend::preprocess (VisionPilot/middleware_recipes/common/backends/
+    tensorrt_backend.cpp:160-177): cv::resize (INTER_LINEAR) on BGR, convertTo(1/255), subtract
+    Scalar(0.406,0.456,0.485), divide Scalar(0.225,0.224,0.229) — BGR-ordered stats, NO channel
+    swap (tensor channel 0 = blue) — then split to CHW."""
+    import numpy as np
+    small = resize_fn(bgr_u8_hwc, 640, 320)
+    x = small.astype(np.float32) * np.float32(1.0 / 255.0)
+    mean = np.array([0.406, 0.456, 0.485], dtype=np.float32)
+    std = np.array([0.225, 0.224, 0.229], dtype=np.float32)
+    x = (x - mean) / std
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(2, 0, 1))).unsqueeze(0)
+
+
+def preprocess_cpp_egolanes(bgr_u8_hwc, resize_fn) -> torch.Tensor:
+    """EgoLanesTensorRTEngine::preprocessEgoLanes (VisionPilot/production_release/src/inference/
+    tensorrt_engine.cpp:190-220): INTER_LINEAR resize, BGR->RGB, convertTo(1/255),
+    (x - MEAN[c]) / STD[c] with RGB stats, CHW."""
+    import numpy as np
+    small = resize_fn(bgr_u8_hwc, 640, 320)[..., ::-1]
+    x = small.astype(np.float32) * np.float32(1.0 / 255.0)
+    x = (x - np.array(MEAN, dtype=np.float32)) / np.array(STD, dtype=np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(2, 0, 1))).unsqueeze(0)
+
+
+def ego_lanes_masks(raw, threshold: float = 0.0):
+    """EgoLanesTensorRTEngine::postProcess (tensorrt_engine.cpp:264-305): three float masks
+    (v > threshold ? 1 : 0) — and the class-id rule of createEgoLanesMaskKernel
+    (common/visualizers/cuda_visualization_kernels.cu:45-75): other > right > left, else 255."""
+    import numpy as np
+    r = np.asarray(raw)
+    masks = (r > threshold).astype(np.float32)
+    ids = np.full(r.shape[1:], 255, dtype=np.uint8)
+    ids[r[0] > 0] = 0
+    ids[r[1] > 0] = 1
+    ids[r[2] > 0] = 2
+    return masks, ids
+
+
+def seg_mask_255(raw):
+    """createMaskKernel / the CPU fallback of RunModelNode::onImage
+    (cuda_visualization_kernels.cu:13-42, ROS2/models/src/run_model_node.cpp:148-172): argmax with
+    strict '>' from -1e9 (first max wins), class 1 -> 255 else 0; single channel: v > 0 -> 255."""
+    import numpy as np
+    r = np.asarray(raw)
+    if r.shape[0] > 1:
+        return np.where(np.argmax(r, axis=0) == 1, 255, 0).astype(np.uint8)
+    return np.where(r[0] > 0, 255, 0).astype(np.uint8)

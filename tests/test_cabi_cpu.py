@@ -1,0 +1,108 @@
+"""CPU-only checks of the shared library: it loads, exports every symbol the headers declare, and
+its host-only pieces (integer resize tables, argument validation, .vpw writer) agree with the
+oracle.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from autoware_vision_pilot_b200 import _lib as L
+from autoware_vision_pilot_b200 import weights as W
+from oracle import resize
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for h in ("vp_b200.h", "vp_b200_ops.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(vpb?_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+@pytest.mark.parametrize("mode,in_size,out_size", [(1, 1920, 640), (1, 1080, 320), (1, 700, 320), (1, 401, 640),
+                                                   (2, 1920, 640), (2, 1080, 320), (2, 660, 320), (2, 517, 640)])
+def test_resize_tables_match_oracle(mode, in_size, out_size):
+    """The C++ host code that builds the kernel's integer coefficient tables reproduces the
+    Pillow / OpenCV restatements exactly (which are themselves pinned against the libraries)."""
+    lib = L.lib()
+    lib.vpb_resize_tables_host.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                           C.c_int, C.POINTER(C.c_int)]
+    bounds = (C.c_int * out_size)()
+    cap = out_size * 64
+    coeffs = (C.c_int * cap)()
+    ks = C.c_int()
+    L.check(lib.vpb_resize_tables_host(mode, in_size, out_size, bounds, coeffs, cap, C.byref(ks)), "tables")
+    k = ks.value
+    got = np.frombuffer(coeffs, dtype=np.int32)[: out_size * k].reshape(out_size, k)
+    if mode == 1:
+        b, cs = resize.pil_coeffs(in_size, out_size)
+        for o in range(out_size):
+            assert bounds[o] == b[o]
+            n = len(cs[o])
+            assert np.array_equal(got[o, :n], cs[o])
+            assert not got[o, n:].any()
+    else:
+        idx, w0, w1 = resize.cv_linear_coeffs(in_size, out_size)
+        assert np.array_equal(np.frombuffer(bounds, dtype=np.int32), idx)
+        assert np.array_equal(got[:, 0], w0) and np.array_equal(got[:, 1], w1)
+
+
+def test_conv_rejects_bad_arguments_without_a_gpu():
+    lib = L.lib()
+    a = L.ConvArgs()
+    a.H, a.W, a.Cin, a.ldi, a.Cout, a.taps, a.phases = 8, 8, 12, 12, 8, 9, 1   # Cin not multiple of 8
+    assert lib.vpb_conv_gemm(C.byref(a), None) == -1
+    assert "multiples of 8" in L.last_error()
+    a.Cin = a.ldi = 16
+    a.taps = 4
+    assert lib.vpb_conv_gemm(C.byref(a), None) == -1
+
+
+def test_vpw_writer_layout(tmp_path):
+    sd = {"a.weight": np.arange(24, dtype=np.float32).reshape(2, 3, 2, 2),
+          "a.num_batches_tracked": np.array(7, dtype=np.int64)}
+    p = W.write_vpw(sd, str(tmp_path / "t.vpw"))
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"VPW1" and struct.unpack("<I", raw[4:8])[0] == 2
+    nl = struct.unpack("<I", raw[8:12])[0]
+    assert raw[12:12 + nl] == b"a.weight"
+    off = 12 + nl
+    dt, nd = struct.unpack("<II", raw[off:off + 8])
+    assert (dt, nd) == (0, 4)
+    dims = struct.unpack("<4I", raw[off + 8:off + 24])
+    assert dims == (2, 3, 2, 2)
+    nbytes = struct.unpack("<Q", raw[off + 24:off + 32])[0]
+    assert nbytes == 96
+    assert np.array_equal(np.frombuffer(raw[off + 32:off + 32 + 96], dtype=np.float32), np.arange(24))
+
+
+def test_infer_helpers_keep_reference_error_behaviour():
+    from autoware_vision_pilot_b200.inference import (DomainSegNetworkInfer, EgoLanesNetworkInfer,
+                                                      Scene3DNetworkInfer, SceneSegNetworkInfer)
+    for K in (SceneSegNetworkInfer, Scene3DNetworkInfer, DomainSegNetworkInfer, EgoLanesNetworkInfer):
+        with pytest.raises(ValueError):
+            K(checkpoint_path="")          # scene_seg_infer.py:32-33
+
+
+def test_engine_create_fails_loudly_without_gpu(tmp_path):
+    """No CPU fallback: on a box without a B200 the engine must refuse, not degrade."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from autoware_vision_pilot_b200 import engine as E
+    with pytest.raises(RuntimeError):
+        E.Engine([E.SCENE_SEG], [str(tmp_path / "missing.vpw")])
