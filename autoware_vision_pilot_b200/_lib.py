@@ -16,6 +16,7 @@ VPB_F16, VPB_BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_SILU, ACT_SIGMOID = 0, 1, 2, 3
 EPI_STORE, EPI_ADD, EPI_MULADD, EPI_FINAL = 0, 1, 2, 3
 FINAL_NONE, FINAL_ARGMAX, FINAL_THRESH, FINAL_EGOLANES = 0, 1, 2, 3
+ALGO_TILE, ALGO_LINEAR = 0, 1
 
 
 class ConvArgs(C.Structure):
@@ -31,6 +32,8 @@ class ConvArgs(C.Structure):
         ("res", C.c_void_p), ("ldr", C.c_int),
         ("out_f32", C.c_void_p), ("out_cls", C.c_void_p),
         ("bn", C.c_int),
+        ("in_pad", C.c_int), ("out_pad", C.c_int), ("res_pad", C.c_int),
+        ("algo", C.c_int), ("dbg_base_offset", C.c_int),
     ]
 
 

@@ -1,4 +1,4 @@
-// conv_gemm.cu — implicit-GEMM convolution on Blackwell tcgen05 tensor cores.
+// conv_gemm.cu — implicit-GEMM convolutions on Blackwell tcgen05 tensor cores.
 //
 // Replaces (reference, all fp32 library calls):
 //   nn.Conv2d 3x3 s1 p1   Models/model_components/scene_neck.py:13-24, scene_seg_head.py:13-19,
@@ -6,22 +6,37 @@
 //   nn.Conv2d 1x1         scene_neck.py:12,17,22 (skip links) and EfficientNet-B0 pointwise convs
 //   nn.ConvTranspose2d k2 s2   scene_neck.py:11,16,21, scene_seg_head.py:11,16
 //
-// Formulation.  Activations are NHWC 16-bit.  For an output tile of 128 pixels
-// (a TH x TW spatial patch) and BN output channels,
-//     D[pixel, n] = sum_{tap} sum_{c} In[pixel + offset(tap), c] * W[tap][n][c]
-// is a GEMM with M = 128, N = BN, K = taps * Cin.  The A operand for one (tap, 64-channel
-// chunk) is a single 4-D TMA box {64 ch, TW, TH, 1} at the shifted coordinate; out-of-range
-// rows/columns are zero-filled by the TMA unit, which IS the convolution's zero padding.
-// The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, exactly
-// the K-major layout tcgen05.mma consumes.  B (weights) is a {64, BN, 1} box of the
-// [tap][Cout][Cin] tensor.  Accumulators live in TMEM (fp32), double-buffered so the
-// epilogue of tile i overlaps the main loop of tile i+1.
+// Two main loops share one epilogue.
 //
-// Warp roles (320 threads, persistent, 1 CTA / SM):
-//   warp 0      TMA producer (one elected lane)
-//   warp 1      tcgen05.mma issuer (one elected lane)
-//   warps 2..9  epilogue: tcgen05.ld -> bias/activation/residual -> 16-bit NHWC stores
-//               (or fp32 planar logits + class map for the heads' last conv).
+// (1) conv_gemm_kernel — "tile" formulation, any of the three op types.
+//     Activations are NHWC 16-bit.  For an output tile of 128 pixels (a TH x TW patch) and BN
+//     output channels,  D[pixel, n] = sum_tap sum_c In[pixel + off(tap), c] * W[tap][n][c]  is a GEMM
+//     with M = 128, N = BN, K = taps*Cin.  The A operand for one (tap, 64-channel chunk) is one 4-D
+//     TMA box {64 ch, TW, TH, 1} at the shifted coordinate; out-of-range rows/columns are
+//     zero-filled by the TMA unit, which IS the convolution's zero padding.
+//
+// (2) conv3x3_lin_kernel — "linear padded" formulation for the 3x3 layers that carry > 90 % of the
+//     FLOPs.  Input and output live in HBM as zero-bordered images [(H+2)*(W+2)][C]; the GEMM M
+//     index is the linear padded pixel index p, so tap (dy,dx) is the constant shift
+//     (dy-1)*(W+2)+(dx-1).  One TMA box of 130 consecutive pixels per (chunk, dy) serves the three
+//     dx taps: the MMA's A descriptor simply starts dx rows (dx*128 B) further into the same
+//     shared-memory segment.  Measured on B200 (scripts/check_base_offset.py): the 128-B swizzle
+//     phase is taken from the absolute shared-memory address, so the descriptor's base_offset
+//     field must stay 0 for these row-shifted views (setting it to dx gives wrong results).
+//     A traffic from L2 drops 9 -> 3.05 loads per chunk and TMA issue count halves; B (weights)
+//     stream through their own ring.  Border pixels are written as zeros, so the output is again
+//     a valid zero-bordered image for the next layer.
+//
+// Both: operands land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma reads
+// through descriptors; fp32 accumulators in TMEM, two of them, so the epilogue of tile i overlaps
+// the main loop of tile i+1; persistent grid; warp-specialised:
+//   warp 0       TMA producer (one elected lane)
+//   warp 1       tcgen05.mma issuer (one elected lane)
+//   warps 2..17  epilogue (4 per TMEM lane quadrant, splitting the 16-column chunks):
+//                tcgen05.ld -> +bias (staged in smem) -> activation -> residual -> 16-bit NHWC
+//                stores (or fp32 planar logits + class map for the heads' last conv).
+//                The first ncu capture (profiles/r1_conv_v1_ncu.md) showed the kernel bound by this
+//                stage, hence 16 warps, a branch-free GELU and no per-element global loads.
 #include "common.cuh"
 #include "conv_gemm.cuh"
 #include <cstdio>
@@ -30,14 +45,128 @@
 
 namespace vpb {
 
-static constexpr int kThreads = 320;
-static constexpr int kEpiWarps = 8;
+static constexpr int kEpiWarps = 16;
+static constexpr int kThreads = 64 + kEpiWarps * 32;
 static constexpr int kMaxStages = 8;
 static constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 ch x 2 B
 static constexpr int kAccStride = 256;         // TMEM columns between the two accumulators
-// 227 KB opt-in limit covers static + dynamic shared memory; keep 2 KB for the static part.
-static constexpr int kMaxDynSmem = 227 * 1024 - 2048;
+// 227 KB opt-in limit covers static + dynamic shared memory; keep 4 KB for the static part.
+static constexpr int kMaxDynSmem = 227 * 1024 - 4096;
+// linear kernel
+static constexpr int kSegRows = 130;                 // 128 pixels + one halo pixel each side
+static constexpr int kSegBytes = 17 * 1024;          // slot size (130*128 = 16640 B used)
+static constexpr int kMaxRing = 16;
 
+// ------------------------------------------------------------------------------------------------
+// Shared epilogue: one accumulator (128 rows x BN fp32 columns in TMEM) -> outputs.
+// ------------------------------------------------------------------------------------------------
+struct EpiPix {
+  bool ok;        // compute and store this row
+  bool zero;      // store zeros instead (border pixel of a padded output)
+  size_t opix;    // pixel index in the output tensor
+  size_t rpix;    // pixel index in the residual tensor
+  size_t fpix;    // pixel index in the planar fp32 / class outputs (FINAL)
+};
+
+template <class E>
+__device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_row, int n0,
+                                              const float* sbias, int part, const EpiPix& px) {
+  const int nchunks = p.BN >> 4;
+  typename E::T* out = reinterpret_cast<typename E::T*>(p.out);
+  const typename E::T* res = reinterpret_cast<const typename E::T*>(p.res);
+  for (int chunk = part; chunk < nchunks; chunk += 4) {
+    uint32_t rr[16];
+    tmem_ld16(t_row + chunk * 16, rr);
+    tmem_ld_wait();
+    const int n = n0 + chunk * 16;
+    const float* sb = sbias + chunk * 16;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + sb[i];
+    // activation switch hoisted out of the element loop (act(0) == 0 for GELU/SiLU keeps the
+    // channel padding zero; sigmoid is masked explicitly)
+    if (p.act == ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = act_gelu(v[i]);
+    } else if (p.act == ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = act_silu(v[i]);
+    } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = (n + i < p.Cout) ? act_sigmoid(v[i]) : 0.f;
+    }
+    if (p.mode == VPB_EPI_FINAL) {
+      if (px.ok && chunk == 0) {
+        const size_t plane = static_cast<size_t>(p.H) * p.W;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < p.Cout) p.out_f32[i * plane + px.fpix] = v[i];
+        if (p.out_cls) {
+          uint8_t cls = 0;
+          if (p.final_kind == VPB_FINAL_ARGMAX) {
+            float best = v[0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i)
+              if (i < p.Cout && v[i] > best) { best = v[i]; cls = static_cast<uint8_t>(i); }
+          } else if (p.final_kind == VPB_FINAL_THRESH) {
+            cls = v[0] > 0.f ? 1 : 0;
+          } else if (p.final_kind == VPB_FINAL_EGOLANES) {
+            cls = (v[2] > 0.f) ? 2 : (v[1] > 0.f) ? 1 : (v[0] > 0.f) ? 0 : 255;
+          }
+          p.out_cls[px.fpix] = cls;
+        }
+      }
+    } else if (px.ok) {
+      if (p.mode == VPB_EPI_ADD || p.mode == VPB_EPI_MULADD) {
+        const typename E::T* rp = res + px.rpix * p.ldr + n;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (n + 8 * j < p.ldr && n + 8 * j < p.ldo) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rp + 8 * j);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = unpack2<E>(rw[i]);
+              float& a = v[8 * j + 2 * i];
+              float& b = v[8 * j + 2 * i + 1];
+              if (p.mode == VPB_EPI_ADD) { a += f.x; b += f.y; }
+              else { a = fmaf(a, f.x, f.x); b = fmaf(b, f.y, f.y); }
+            }
+          }
+        }
+      }
+      typename E::T* op = out + px.opix * p.ldo + n;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (n + 8 * j < p.ldo) {
+          uint4 o;
+          o.x = pack2<E>(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack2<E>(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack2<E>(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack2<E>(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(op + 8 * j) = o;
+        }
+      }
+    } else if (px.zero) {
+      typename E::T* op = out + px.opix * p.ldo + n;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (n + 8 * j < p.ldo) *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+__device__ __forceinline__ void stage_bias(const ConvKParams& p, float* dst, int etid, int n0) {
+  if (etid < p.BN) {
+    const int nn = n0 + etid;
+    dst[etid] = (p.bias && nn < p.Cout) ? __ldg(p.bias + nn) : 0.f;
+  }
+  asm volatile("bar.sync 1, 512;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// (1) tile formulation
+// ------------------------------------------------------------------------------------------------
 template <class E>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -48,6 +177,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_holder;
+  __shared__ float s_bias[2][256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,17 +275,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
     }
   } else {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;           // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2; // which interleaved set of 16-column chunks
-    const int row = q * 32 + lane;    // accumulator row == pixel within the tile
+    const int q = warp & 3;            // TMEM lane quadrant this warp may read
+    const int part = (warp - 2) >> 2;  // which interleaved set of 16-column chunks (0..3)
+    const int etid = threadIdx.x - 64; // 0..511 among the epilogue threads
+    const int row = q * 32 + lane;     // accumulator row == pixel within the tile
     const int lh = row >> p.tw_shift;
     const int lw = row & (p.TW - 1);
-    const int nchunks = p.BN >> 4;
-    const int Ho = (p.phases > 1) ? 2 * p.H : p.H;
     const int Wo = (p.phases > 1) ? 2 * p.W : p.W;
-    (void)Ho;
-    typename E::T* out = reinterpret_cast<typename E::T*>(p.out);
-    const typename E::T* res = reinterpret_cast<const typename E::T*>(p.res);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -167,88 +293,172 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
       const int twi = r % p.tiles_w;
       const int thi = r / p.tiles_w;
       const int h = thi * p.TH + lh, w = twi * p.TW + lw, n0 = nt * p.BN;
-      const bool pix_ok = (h < p.H) && (w < p.W);
       const int oh = (p.phases > 1) ? 2 * h + (ph >> 1) : h;
       const int ow = (p.phases > 1) ? 2 * w + (ph & 1) : w;
-      const size_t opix = static_cast<size_t>(oh) * Wo + ow;
+      EpiPix px;
+      px.ok = (h < p.H) && (w < p.W);
+      px.zero = false;
+      px.opix = static_cast<size_t>(oh + p.out_pad) * (Wo + 2 * p.out_pad) + (ow + p.out_pad);
+      px.rpix = static_cast<size_t>(oh + p.res_pad) * (Wo + 2 * p.res_pad) + (ow + p.res_pad);
+      px.fpix = static_cast<size_t>(h) * p.W + w;
 
+      stage_bias(p, s_bias[as], etid, n0);
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+    }
+  }
 
-      for (int chunk = half; chunk < nchunks; chunk += 2) {
-        uint32_t rr[16];
-        tmem_ld16(t_row + chunk * 16, rr);
-        tmem_ld_wait();
-        const int n = n0 + chunk * 16;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int nn = n + i;
-          float x = __uint_as_float(rr[i]);
-          if (nn < p.Cout) {
-            if (p.bias) x += __ldg(p.bias + nn);
-            x = apply_act(x, p.act);
-          } else {
-            x = 0.f;
-          }
-          v[i] = x;
-        }
-        if (p.mode == VPB_EPI_FINAL) {
-          if (pix_ok && chunk == 0) {
-            const size_t plane = static_cast<size_t>(p.H) * p.W;
-            const size_t pix = static_cast<size_t>(h) * p.W + w;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < p.Cout) p.out_f32[i * plane + pix] = v[i];
-            if (p.out_cls) {
-              uint8_t cls = 0;
-              if (p.final_kind == VPB_FINAL_ARGMAX) {
-                float best = v[0];
-#pragma unroll
-                for (int i = 1; i < 16; ++i)
-                  if (i < p.Cout && v[i] > best) { best = v[i]; cls = static_cast<uint8_t>(i); }
-              } else if (p.final_kind == VPB_FINAL_THRESH) {
-                cls = v[0] > 0.f ? 1 : 0;
-              } else if (p.final_kind == VPB_FINAL_EGOLANES) {
-                cls = (v[2] > 0.f) ? 2 : (v[1] > 0.f) ? 1 : (v[0] > 0.f) ? 0 : 255;
-              }
-              p.out_cls[pix] = cls;
-            }
-          }
-        } else if (pix_ok) {
-          if (p.mode == VPB_EPI_ADD || p.mode == VPB_EPI_MULADD) {
-            const typename E::T* rp = res + opix * p.ldr + n;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              if (n + 8 * j < p.ldr && n + 8 * j < p.ldo) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(rp + 8 * j);
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = unpack2<E>(rw[i]);
-                  float& a = v[8 * j + 2 * i];
-                  float& b = v[8 * j + 2 * i + 1];
-                  if (p.mode == VPB_EPI_ADD) { a += f.x; b += f.y; }
-                  else { a = a * f.x + f.x; b = b * f.y + f.y; }
-                }
-              }
-            }
-          }
-          typename E::T* op = out + opix * p.ldo + n;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (n + 8 * j < p.ldo) {
-              uint4 o;
-              o.x = pack2<E>(v[8 * j + 0], v[8 * j + 1]);
-              o.y = pack2<E>(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack2<E>(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack2<E>(v[8 * j + 6], v[8 * j + 7]);
-              *reinterpret_cast<uint4*>(op + 8 * j) = o;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (2) linear padded formulation (3x3 only)
+// ------------------------------------------------------------------------------------------------
+template <class E>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
+                   const __grid_constant__ CUtensorMap mapB, const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kMaxRing], a_empty[kMaxRing];
+  __shared__ __align__(8) uint64_t b_full[kMaxRing], b_empty[kMaxRing];
+  __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_holder;
+  __shared__ float s_bias[2][256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t b_base = smem_base + p.na * kSegBytes;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.na; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tmem_holder), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+        const int p0 = mt * 128, n0 = nt * p.BN;
+        for (int c = 0; c < p.kchunks; ++c) {
+          for (int dy = 0; dy < 3; ++dy) {
+            mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1u);
+            const uint32_t af = smem_u32(&a_full[sa]);
+            mbar_arrive_expect_tx(af, kSegRows * 128);
+            // 130 consecutive padded pixels starting one pixel left of the tile in row (dy-1)
+            tma_load_2d(smem_base + sa * kSegBytes, &mapA, af, c * 64, p0 + (dy - 1) * p.WP - 1);
+            if (++sa == p.na) { sa = 0; pa ^= 1u; }
+            for (int dx = 0; dx < 3; ++dx) {
+              mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1u);
+              const uint32_t bf = smem_u32(&b_full[sb]);
+              mbar_arrive_expect_tx(bf, b_bytes);
+              tma_load_3d(b_base + sb * b_bytes, &mapB, bf, c * 64, n0, dy * 3 + dx);
+              if (++sb == p.nb) { sb = 0; pb ^= 1u; }
             }
           }
         }
       }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(E::kUmmaFmt, 128, p.BN);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        uint32_t first = 1;
+        for (int c = 0; c < p.kchunks; ++c) {
+          const int kvalid = min(64, p.Cin - c * 64);
+          const int ksteps = (kvalid + 15) >> 4;
+          for (int dy = 0; dy < 3; ++dy) {
+            mbar_wait(smem_u32(&a_full[sa]), pa);
+            const uint32_t seg = smem_base + sa * kSegBytes;
+            for (int dx = 0; dx < 3; ++dx) {
+              mbar_wait(smem_u32(&b_full[sb]), pb);
+              tc_fence_after();
+              // tap view: same segment, dx pixel rows further in (swizzle phase follows the address)
+              const uint64_t adesc =
+                  umma_desc_k128(seg + dx * 128, p.desc_bo ? static_cast<uint32_t>(dx) : 0u);
+              const uint64_t bdesc = umma_desc_k128(b_base + sb * b_bytes);
+              for (int kk = 0; kk < ksteps; ++kk) {
+                umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(smem_u32(&b_empty[sb]));
+              if (++sb == p.nb) { sb = 0; pb ^= 1u; }
+            }
+            umma_commit(smem_u32(&a_empty[sa]));
+            if (++sa == p.na) { sa = 0; pa ^= 1u; }
+          }
+        }
+        umma_commit(smem_u32(&bar_tfull[as]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+      const int n0 = nt * p.BN;
+      const int pp = mt * 128 + row;          // linear padded pixel index
+      const int y = pp / p.WP, x = pp - y * p.WP;
+      const bool inside = (pp < p.NP) && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
+      EpiPix px;
+      px.ok = inside;
+      px.zero = (pp < p.NP) && !inside && p.out_pad;
+      const size_t upix = static_cast<size_t>(y - 1) * p.W + (x - 1);   // unpadded index (if inside)
+      px.opix = p.out_pad ? static_cast<size_t>(pp) : upix;
+      px.rpix = p.res_pad ? static_cast<size_t>(pp) : upix;
+      px.fpix = upix;
+
+      stage_bias(p, s_bias[as], etid, n0);
+      mbar_wait(smem_u32(&bar_tfull[as]), aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
@@ -313,6 +523,11 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     vpb_set_error("conv: unsupported taps=%d phases=%d", a->taps, a->phases);
     return VPB_ERR_ARG;
   }
+  const bool lin = a->algo == VPB_ALGO_LINEAR;
+  if (lin && (a->taps != 9 || !a->in_pad)) {
+    vpb_set_error("conv: the linear-padded algorithm needs a 3x3 conv on a zero-bordered input");
+    return VPB_ERR_ARG;
+  }
   if (a->mode == VPB_EPI_FINAL) {
     if (a->Cout > 16 || !a->out_f32) {
       vpb_set_error("conv: FINAL mode needs Cout<=16 and out_f32");
@@ -337,53 +552,80 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   ConvKParams& p = plan->p;
   p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout;
   p.taps = a->taps; p.phases = a->phases;
-  // spatial tile: minimise padded pixels, prefer wide tiles
-  int best_tw = 128; long best_cost = -1;
-  for (int tw = 128; tw >= 8; tw >>= 1) {
-    const int th = 128 / tw;
-    const long cost = static_cast<long>((a->H + th - 1) / th) * ((a->W + tw - 1) / tw);
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
-  }
-  p.TW = best_tw; p.TH = 128 / best_tw;
-  p.tw_shift = 0; while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+  p.in_pad = a->in_pad ? 1 : 0; p.out_pad = a->out_pad ? 1 : 0; p.res_pad = a->res_pad ? 1 : 0;
+  p.lin = lin ? 1 : 0;
+  p.desc_bo = a->dbg_base_offset ? 1 : 0;
+  p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
   if (p.BN % 16 || p.BN > 256 || p.BN < 16) {
     vpb_set_error("conv: bad BN %d", p.BN);
     return VPB_ERR_ARG;
   }
-  p.tiles_h = (a->H + p.TH - 1) / p.TH;
-  p.tiles_w = (a->W + p.TW - 1) / p.TW;
   p.tiles_n = (a->Cout + p.BN - 1) / p.BN;
-  p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * p.phases;
   p.kchunks = (a->Cin + 63) / 64;
-  const size_t stage_bytes = kATileBytes + static_cast<size_t>(p.BN) * 128;
-  int stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes);
-  p.stages = std::max(2, std::min(stages, kMaxStages));
+  const size_t b_bytes = static_cast<size_t>(p.BN) * 128;
+  if (lin) {
+    p.tiles_m = (p.NP + 127) / 128;
+    p.total_tiles = p.tiles_m * p.tiles_n;
+    p.na = p.BN >= 256 ? 3 : 4;
+    const size_t left = kMaxDynSmem - 1024 - static_cast<size_t>(p.na) * kSegBytes;
+    p.nb = static_cast<int>(std::min<size_t>(kMaxRing, left / b_bytes));
+    if (p.nb < 3) { vpb_set_error("conv: no room for the weight ring"); return VPB_ERR_ARG; }
+    plan->smem_bytes = static_cast<size_t>(p.na) * kSegBytes + p.nb * b_bytes + 1024;
+    p.TW = 128; p.TH = 1; p.tw_shift = 7;
+  } else {
+    // spatial tile: minimise padded pixels, prefer wide tiles
+    int best_tw = 128; long best_cost = -1;
+    for (int tw = 128; tw >= 8; tw >>= 1) {
+      const int th = 128 / tw;
+      const long cost = static_cast<long>((a->H + th - 1) / th) * ((a->W + tw - 1) / tw);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
+    }
+    p.TW = best_tw; p.TH = 128 / best_tw;
+    p.tw_shift = 0; while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+    p.tiles_h = (a->H + p.TH - 1) / p.TH;
+    p.tiles_w = (a->W + p.TW - 1) / p.TW;
+    p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * p.phases;
+    const size_t stage_bytes = kATileBytes + b_bytes;
+    int stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes);
+    p.stages = std::max(2, std::min(stages, kMaxStages));
+    plan->smem_bytes = p.stages * stage_bytes + 1024;
+  }
   p.act = a->act; p.mode = a->mode; p.final_kind = a->final_kind;
   p.bias = a->bias; p.out = a->out; p.ldo = a->ldo; p.res = a->res; p.ldr = a->ldr;
   p.out_f32 = a->out_f32; p.out_cls = a->out_cls;
   plan->dtype = a->dtype;
-  plan->smem_bytes = p.stages * stage_bytes + 1024;
   plan->grid = std::min(p.total_tiles, device_sm_count());
   plan->flops = 2.0 * a->H * a->W * static_cast<double>(a->Cout) * a->Cin * a->taps * a->phases;
 
   const CUtensorMapDataType dt =
       a->dtype == VPB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  {
+  CUresult r;
+  if (lin) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(p.NP)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(a->ldi) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kSegRows)};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(&plan->mapA, dt, 2, const_cast<void*>(a->in), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    // a zero-bordered input is addressed through its interior: base at pixel (1,1), padded pitch
+    const int pad = p.in_pad;
+    const size_t pitch = static_cast<size_t>(a->W + 2 * pad) * a->ldi * 2;
+    const uint8_t* base = static_cast<const uint8_t*>(a->in) + pad * pitch + static_cast<size_t>(pad) * a->ldi * 2;
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->W),
                           static_cast<cuuint64_t>(a->H), 1};
-    cuuint64_t strides[3] = {static_cast<cuuint64_t>(a->ldi) * 2,
-                             static_cast<cuuint64_t>(a->ldi) * 2 * a->W,
-                             static_cast<cuuint64_t>(a->ldi) * 2 * a->W * a->H};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(a->ldi) * 2, pitch, pitch * (a->H + 2 * pad)};
     cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.TW), static_cast<cuuint32_t>(p.TH), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&plan->mapA, dt, 4, const_cast<void*>(a->in), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      vpb_set_error("conv: cuTensorMapEncodeTiled(A) failed: %d", static_cast<int>(r));
-      return VPB_ERR_CUDA;
-    }
+    r = enc(&plan->mapA, dt, 4, const_cast<uint8_t*>(base), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    vpb_set_error("conv: cuTensorMapEncodeTiled(A) failed: %d", static_cast<int>(r));
+    return VPB_ERR_CUDA;
   }
   {
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->Cout),
@@ -392,9 +634,9 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
                              static_cast<cuuint64_t>(a->Cin) * 2 * a->Cout};
     cuuint32_t box[3] = {64, static_cast<cuuint32_t>(p.BN), 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&plan->mapB, dt, 3, const_cast<void*>(a->w), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    r = enc(&plan->mapB, dt, 3, const_cast<void*>(a->w), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       vpb_set_error("conv: cuTensorMapEncodeTiled(B) failed: %d", static_cast<int>(r));
       return VPB_ERR_CUDA;
@@ -404,23 +646,22 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
 }
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
-  static bool attr_set[2] = {false, false};
-  const int di = plan->dtype == VPB_BF16 ? 1 : 0;
-  if (!attr_set[di]) {
-    if (di == 0)
-      VPB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<F16>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    else
-      VPB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BF16>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attr_set[di] = true;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    VPB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_lin_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_lin_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    attr_set = true;
   }
-  if (di == 0)
-    conv_gemm_kernel<F16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA, plan->mapB,
-                                                                               plan->p);
-  else
-    conv_gemm_kernel<BF16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA,
-                                                                                plan->mapB, plan->p);
+  const bool bf = plan->dtype == VPB_BF16;
+  if (plan->p.lin) {
+    if (bf) conv3x3_lin_kernel<BF16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA, plan->mapB, plan->p);
+    else conv3x3_lin_kernel<F16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA, plan->mapB, plan->p);
+  } else {
+    if (bf) conv_gemm_kernel<BF16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA, plan->mapB, plan->p);
+    else conv_gemm_kernel<F16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA, plan->mapB, plan->p);
+  }
   VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
 }

@@ -71,8 +71,9 @@ DwGeom dw_geometry(int H, int W, int C, int k, int stride) {
   g.PPB = std::max(1, 256 / g.G);
   g.threads = g.G * g.PPB;
   const int npix = g.Ho * g.Wo;
-  // ~4 waves of blocks over 148 SMs, each block a contiguous pixel range (multiple of PPB)
-  int ppb = (npix + 148 * 4 - 1) / (148 * 4);
+  // ~2 blocks per SM, each block a contiguous pixel range (multiple of PPB); few blocks keep the
+  // number of pooling atomics (and their contention on a handful of cache lines) low
+  int ppb = (npix + 148 * 2 - 1) / (148 * 2);
   ppb = (ppb + g.PPB - 1) / g.PPB * g.PPB;
   g.pix_per_block = std::max(ppb, g.PPB);
   g.nblocks = (npix + g.pix_per_block - 1) / g.pix_per_block;
@@ -136,7 +137,8 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict_
     for (int i = 0; i < 8; ++i) {
       float s = 0.f;
       for (int q = 0; q < PPB; ++q) s += red[q * C + cg * 8 + i];
-      atomicAdd(reinterpret_cast<unsigned long long*>(gap_acc + cg * 8 + i),
+      // kGapReplicas copies of the accumulator spread the atomics over more L2 lines
+      atomicAdd(reinterpret_cast<unsigned long long*>(gap_acc + (blockIdx.x % kGapReplicas) * C + cg * 8 + i),
                 static_cast<unsigned long long>(__float2ll_rn(s * 16777216.0f)));
     }
   }
@@ -144,12 +146,14 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict_
 
 // ------------------------------------------------------------------ squeeze-excitation gate
 // Every block recomputes the (tiny) gate, then scales its slice of the projection weights.
+// The kernel is a chain of four dependent phases, each bound by one L2 round trip, so every phase
+// issues all of its loads before consuming them (float4 rows, unrolled loops).
 template <class E>
-__global__ void __launch_bounds__(256) se_scale_kernel(const long long* __restrict__ gap_acc,
+__global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restrict__ gap_acc,
                                                         float inv_hw, int C, int sq,
                                                         const float* __restrict__ w1,
                                                         const float* __restrict__ b1,
-                                                        const float* __restrict__ w2,
+                                                        const float* __restrict__ w2t,
                                                         const float* __restrict__ b2,
                                                         const float* __restrict__ w_proj, int Cout,
                                                         typename E::T* __restrict__ w_scaled,
@@ -158,13 +162,24 @@ __global__ void __launch_bounds__(256) se_scale_kernel(const long long* __restri
   float* mean = sm;        // [C]
   float* hid = sm + C;     // [sq]
   float* gate = hid + sq;  // [C]
-  for (int c = threadIdx.x; c < C; c += blockDim.x)
-    mean[c] = static_cast<float>(static_cast<double>(gap_acc[c]) * (1.0 / 16777216.0)) * inv_hw;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    long long a = 0;
+#pragma unroll
+    for (int r = 0; r < kGapReplicas; ++r) a += gap_acc[r * C + c];
+    mean[c] = static_cast<float>(static_cast<double>(a) * (1.0 / 16777216.0)) * inv_hw;
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int C4 = C >> 2;
   for (int j = warp; j < sq; j += nw) {
+    const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j) * C);
+    const float4* mr = reinterpret_cast<const float4*>(mean);
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(w1[static_cast<size_t>(j) * C + c], mean[c], s);
+#pragma unroll 12
+    for (int c = lane; c < C4; c += 32) {
+      const float4 a = __ldg(wr + c), m = mr[c];
+      s = fmaf(a.x, m.x, fmaf(a.y, m.y, fmaf(a.z, m.z, fmaf(a.w, m.w, s))));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) hid[j] = act_silu(s + b1[j]);
@@ -172,16 +187,24 @@ __global__ void __launch_bounds__(256) se_scale_kernel(const long long* __restri
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = b2[c];
-    for (int j = 0; j < sq; ++j) s = fmaf(w2[static_cast<size_t>(c) * sq + j], hid[j], s);
+#pragma unroll 16
+    for (int j = 0; j < sq; ++j) s = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), hid[j], s);
     const float g = 1.0f / (1.0f + expf(-s));
     gate[c] = g;
     if (scale_out && blockIdx.x == 0) scale_out[c] = g;
   }
   __syncthreads();
-  const int total = Cout * C;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int k = i % C;
-    w_scaled[i] = from_f32<E>(w_proj[i] * gate[k]);
+  // scaled projection weights, 8 elements (one 16-byte store) per thread-iteration
+  const int C8 = C >> 3, total8 = Cout * C8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += gridDim.x * blockDim.x) {
+    const int k8 = (i % C8) * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w_proj) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w_proj) + 2 * i + 1);
+    const float* g = gate + k8;
+    uint4 o;
+    o.x = pack2<E>(a.x * g[0], a.y * g[1]); o.y = pack2<E>(a.z * g[2], a.w * g[3]);
+    o.z = pack2<E>(b.x * g[4], b.y * g[5]); o.w = pack2<E>(b.z * g[6], b.w * g[7]);
+    reinterpret_cast<uint4*>(w_scaled)[i] = o;
   }
 }
 
@@ -222,7 +245,7 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
 template <class E>
 __global__ void ctx_conv1_kernel(const float* __restrict__ in, int H, int W,
                                  const float* __restrict__ w, const float* __restrict__ b, int Cout,
-                                 typename E::T* __restrict__ out) {
+                                 typename E::T* __restrict__ out, int out_pad) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= H * W * Cout) return;
   const int co = idx % Cout, pix = idx / Cout;
@@ -235,7 +258,7 @@ __global__ void ctx_conv1_kernel(const float* __restrict__ in, int H, int W,
       const int iy = y - 1 + ky, ix = x - 1 + kx;
       if (iy >= 0 && iy < H && ix >= 0 && ix < W) s = fmaf(in[iy * W + ix], w[co * 9 + ky * 3 + kx], s);
     }
-  out[idx] = from_f32<E>(act_gelu(s));
+  out[(static_cast<size_t>(y + out_pad) * (W + 2 * out_pad) + (x + out_pad)) * Cout + co] = from_f32<E>(act_gelu(s));
 }
 
 // ------------------------------------------------------------------ max-pool feature fusion
@@ -337,13 +360,13 @@ extern "C" int vpb_se_scale(int dtype, const long long* gap_acc, int HW, int C, 
                             void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = (2 * static_cast<size_t>(C) + sq) * sizeof(float);
-  const int grid = std::max(1, std::min(32, (Cout * C + 8191) / 8192));
+  const int grid = std::max(1, std::min(48, (Cout * C / 8 + 1023) / 1024));
   if (dtype == VPB_BF16)
-    se_scale_kernel<BF16><<<grid, 256, smem, st>>>(gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
+    se_scale_kernel<BF16><<<grid, 512, smem, st>>>(gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
                                                    w_proj, Cout, static_cast<__nv_bfloat16*>(w_scaled),
                                                    scale_out);
   else
-    se_scale_kernel<F16><<<grid, 256, smem, st>>>(gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
+    se_scale_kernel<F16><<<grid, 512, smem, st>>>(gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
                                                   w_proj, Cout, static_cast<__half*>(w_scaled), scale_out);
   VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
@@ -367,13 +390,13 @@ extern "C" int vpb_linear(const float* x, const float* w, const float* b, int in
 }
 
 extern "C" int vpb_ctx_conv1(int dtype, const float* in, int H, int W, const float* w, const float* b,
-                             int Cout, void* out, void* stream) {
+                             int Cout, void* out, int out_pad, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = H * W * Cout;
   if (dtype == VPB_BF16)
-    ctx_conv1_kernel<BF16><<<(n + 255) / 256, 256, 0, st>>>(in, H, W, w, b, Cout, static_cast<__nv_bfloat16*>(out));
+    ctx_conv1_kernel<BF16><<<(n + 255) / 256, 256, 0, st>>>(in, H, W, w, b, Cout, static_cast<__nv_bfloat16*>(out), out_pad);
   else
-    ctx_conv1_kernel<F16><<<(n + 255) / 256, 256, 0, st>>>(in, H, W, w, b, Cout, static_cast<__half*>(out));
+    ctx_conv1_kernel<F16><<<(n + 255) / 256, 256, 0, st>>>(in, H, W, w, b, Cout, static_cast<__half*>(out), out_pad);
   VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
 }

@@ -83,9 +83,9 @@ static uint64_t hash_prefix(const WeightMap& w, const std::string& pfx) {
 }
 
 // =============================================================== engine
-struct Tens {  // NHWC 16-bit activation, channel stride == C
-  void* p = nullptr; int H = 0, W = 0, C = 0;
-  size_t bytes() const { return static_cast<size_t>(H) * W * C * 2; }
+struct Tens {  // NHWC 16-bit activation, channel stride == C; pad = 1: zero-bordered [(H+2)*(W+2)][C]
+  void* p = nullptr; int H = 0, W = 0, C = 0, pad = 0;
+  size_t bytes() const { return static_cast<size_t>(H + 2 * pad) * (W + 2 * pad) * C * 2; }
 };
 
 struct OpRec {
@@ -136,17 +136,20 @@ struct vp_engine {
   int shared_encoders = 0, shared_trunks = 0;
   // SE pooling accumulators of every MBConv block: one arena, zeroed by one memset per frame
   long long* d_gap = nullptr; size_t gap_used = 0;
-  static constexpr size_t kGapCap = 64 * 1024;   // int64 slots (16 blocks x <=1152 ch per encoder)
+  static constexpr size_t kGapCap = 512 * 1024;  // int64 slots (16 blocks x <=1152 ch x 8 replicas per encoder)
   long long* gap_alloc(int C) {
     if (!d_gap) d_gap = static_cast<long long*>(dalloc(kGapCap * 8, false));
-    if (gap_used + C > kGapCap) return nullptr;
+    const size_t need = static_cast<size_t>(C) * kGapReplicas;
+    if (gap_used + need > kGapCap) return nullptr;
     long long* p = d_gap + gap_used;
-    gap_used += (C + 31) / 32 * 32;
+    gap_used += (need + 31) / 32 * 32;
     return p;
   }
   // graph
   cudaGraphExec_t gexec = nullptr;
+  cudaGraph_t graph = nullptr;           // kept alive: g_pre_node is a handle into it
   int g_h = 0, g_w = 0, g_stride = 0; const uint8_t* g_src = nullptr;
+  cudaGraphNode_t g_pre_node = nullptr;  // the captured pre-process kernel node (re-pointed per frame)
   // module caches for sharing
   struct EncOut { Tens f[5]; };
   std::map<uint64_t, EncOut> enc_cache;
@@ -154,6 +157,7 @@ struct vp_engine {
 
   ~vp_engine() {
     if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
     for (void* p : dev_allocs) cudaFree(p);
     for (void* p : host_allocs) cudaFreeHost(p);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -168,8 +172,8 @@ struct vp_engine {
     (is_weight ? weight_bytes : act_bytes) += bytes;
     return p;
   }
-  Tens act_alloc(int H, int W, int C) {
-    Tens a; a.H = H; a.W = W; a.C = C;
+  Tens act_alloc(int H, int W, int C, int pad = 0) {
+    Tens a; a.H = H; a.W = W; a.C = C; a.pad = pad;
     a.p = dalloc(a.bytes(), false);
     return a;
   }
@@ -197,8 +201,11 @@ struct vp_engine {
     a.dtype = dtype; a.H = in.H; a.W = in.W; a.Cin = in.C; a.ldi = in.C;
     a.Cout = Cout; a.taps = taps; a.phases = phases; a.act = act; a.mode = mode;
     a.final_kind = final_kind; a.in = in.p; a.w = w; a.bias = bias;
-    if (out) { a.out = out->p; a.ldo = out->C; }
-    if (res) { a.res = res->p; a.ldr = res->C; }
+    a.in_pad = in.pad;
+    if (out) { a.out = out->p; a.ldo = out->C; a.out_pad = out->pad; }
+    if (res) { a.res = res->p; a.ldr = res->C; a.res_pad = res->pad; }
+    // 3x3 on a zero-bordered input -> linear-padded kernel (one TMA segment per kernel row)
+    a.algo = (taps == 9 && in.pad) ? VPB_ALGO_LINEAR : VPB_ALGO_TILE;
     a.out_f32 = out_f32; a.out_cls = out_cls;
     auto plan = std::make_unique<ConvPlan>();
     int rc = conv_plan_build(&a, plan.get());
@@ -330,7 +337,11 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
                        *f2 = find_w(w, sp + "fc2.weight"), *b2 = find_w(w, sp + "fc2.bias");
       const HostTensor* pw = find_w(w, bp + std::to_string(bi + 2) + ".0.weight");
       if (!f1 || !b1 || !f2 || !b2 || !pw || !bn_fold(w, bp + std::to_string(bi + 2) + ".1.", cout, s, t)) return VPB_ERR_IO;
-      float *d_f1 = e.upload_f32(f1->f), *d_b1 = e.upload_f32(b1->f), *d_f2 = e.upload_f32(f2->f), *d_b2 = e.upload_f32(b2->f);
+      std::vector<float> f2t(f2->f.size());   // fc2 [C][sq] -> [sq][C] so the gate kernel reads it coalesced
+      for (int c = 0; c < ce; ++c)
+        for (int j = 0; j < sq; ++j) f2t[static_cast<size_t>(j) * ce + c] = f2->f[static_cast<size_t>(c) * sq + j];
+      float *d_f1 = e.upload_f32(f1->f), *d_b1 = e.upload_f32(b1->f), *d_f2 = e.upload_f32(f2t), *d_b2 = e.upload_f32(b2->f);
+      if (!d_part) { vpb_set_error("SE accumulator arena exhausted"); return VPB_ERR_STATE; }
       std::vector<float> proj(pw->f.size());
       for (int co = 0; co < cout; ++co)
         for (int c = 0; c < ce; ++c) proj[static_cast<size_t>(co) * ce + c] = pw->f[static_cast<size_t>(co) * ce + c] * s[co];
@@ -373,7 +384,7 @@ static int conv_layer(vp_engine& e, const WeightMap& w, const std::string& key, 
   if (wt->dims[1] != in.C) { vpb_set_error("%s: Cin %d != input channels %d", key.c_str(), wt->dims[1], in.C); return VPB_ERR_ARG; }
   void* dw_ = e.upload_16(pack_conv(*wt, nullptr));
   float* db = e.upload_f32(bt->f);
-  if (!out->p) *out = e.act_alloc(in.H, in.W, (Cout + 7) / 8 * 8);
+  if (!out->p) *out = e.act_alloc(in.H, in.W, (Cout + 7) / 8 * 8, /*pad=*/1);
   return e.add_conv(name, in, Cout, taps, 1, dw_, db, act, mode, out, res);
 }
 
@@ -384,7 +395,7 @@ static int up_skip(vp_engine& e, const WeightMap& w, const std::string& p, int i
   const HostTensor *ut = find_w(w, uk + ".weight"), *ub = find_w(w, uk + ".bias");
   if (!ut || !ub) return VPB_ERR_IO;
   const int Cout = ut->dims[1];
-  *out = e.act_alloc(in.H * 2, in.W * 2, Cout);
+  *out = e.act_alloc(in.H * 2, in.W * 2, Cout, /*pad=*/1);
   if (skip) {
     int rc = conv_layer(e, w, p + "skip_link_layer_" + std::to_string(i), tag + "skip" + std::to_string(i), *skip, 1,
                         ACT_NONE, VPB_EPI_STORE, out, nullptr);
@@ -423,10 +434,10 @@ static int build_context(vp_engine& e, const WeightMap& w, const std::string& p,
   const HostTensor *w3 = find_w(w, p + "context_layer_3.weight"), *b3 = find_w(w, p + "context_layer_3.bias");
   if (!w3 || !b3) return VPB_ERR_IO;
   float *d_w3 = e.upload_f32(w3->f), *d_b3 = e.upload_f32(b3->f);
-  Tens c4 = e.act_alloc(feat.H, feat.W, 128);
+  Tens c4 = e.act_alloc(feat.H, feat.W, 128, /*pad=*/1);
   {
     const float* xin = cur; void* o = c4.p; const int H = feat.H, W = feat.W;
-    e.add_op(tag + "ctx3", [=](cudaStream_t st) { return vpb_ctx_conv1(dt, xin, H, W, d_w3, d_b3, 128, o, st); },
+    e.add_op(tag + "ctx3", [=](cudaStream_t st) { return vpb_ctx_conv1(dt, xin, H, W, d_w3, d_b3, 128, o, 1, st); },
              2.0 * HW * 128 * 9);
   }
   Tens c5, c6;
@@ -434,7 +445,7 @@ static int build_context(vp_engine& e, const WeightMap& w, const std::string& p,
   if (rc) return rc;
   rc = conv_layer(e, w, p + "context_layer_5", tag + "ctx5", c5, 9, ACT_GELU, VPB_EPI_STORE, &c6, nullptr);
   if (rc) return rc;
-  *ctx = e.act_alloc(feat.H, feat.W, C);
+  *ctx = e.act_alloc(feat.H, feat.W, C, /*pad=*/1);
   return conv_layer(e, w, p + "context_layer_6", tag + "ctx6", c6, 9, ACT_GELU, VPB_EPI_MULADD, ctx, &feat);
 }
 
@@ -567,8 +578,15 @@ static int enqueue_frame(vp_engine& e, const uint8_t* src_dev, int h, int w, int
   int rc = e.pre.configure(h, w, e.cfg.resize_mode);
   if (rc) return rc;
   if (!e.cfg.use_graph) return launch_all(e, src_dev, stride, e.stream);
+  if (e.gexec && e.g_h == h && e.g_w == w && e.g_stride == stride && e.g_src != src_dev && e.g_pre_node) {
+    // same geometry, different frame buffer: re-point the pre-process node instead of re-capturing
+    rc = e.pre.update_graph_node(e.gexec, e.g_pre_node, src_dev, stride, e.cfg.convention, e.dtype, e.d_pre, e.d_resized);
+    if (rc) return rc;
+    e.g_src = src_dev;
+  }
   if (!e.gexec || e.g_h != h || e.g_w != w || e.g_stride != stride || e.g_src != src_dev) {
     if (e.gexec) { cudaGraphExecDestroy(e.gexec); e.gexec = nullptr; }
+    e.g_pre_node = nullptr;
     // warm (sets function attributes outside capture), then capture
     rc = launch_all(e, src_dev, stride, e.stream);
     if (rc) return rc;
@@ -579,8 +597,24 @@ static int enqueue_frame(vp_engine& e, const uint8_t* src_dev, int h, int w, int
     cudaError_t ce = cudaStreamEndCapture(e.stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (ce != cudaSuccess) { vpb_set_error("graph capture failed: %s", cudaGetErrorString(ce)); return VPB_ERR_CUDA; }
+    {  // locate the pre-process kernel node
+      size_t nn = 0;
+      cudaGraphGetNodes(g, nullptr, &nn);
+      std::vector<cudaGraphNode_t> nodes(nn);
+      cudaGraphGetNodes(g, nodes.data(), &nn);
+      for (size_t i = 0; i < nn; ++i) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp{};
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && e.pre.owns_kernel(kp.func, e.dtype)) {
+          e.g_pre_node = nodes[i];
+          break;
+        }
+      }
+    }
     ce = cudaGraphInstantiate(&e.gexec, g, 0);
-    cudaGraphDestroy(g);
+    if (e.graph) cudaGraphDestroy(e.graph);
+    e.graph = g;
     if (ce != cudaSuccess) { vpb_set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); return VPB_ERR_CUDA; }
     e.g_h = h; e.g_w = w; e.g_stride = stride; e.g_src = src_dev;
   }
@@ -753,12 +787,13 @@ extern "C" int vp_engine_read_resized(vp_engine* e, uint8_t* dst) {
 }
 
 namespace vpb {
-template <class T> __global__ void tap_to_f32_nchw(const T* in, int H, int W, int C, int Cvalid, float* out) {
+template <class T> __global__ void tap_to_f32_nchw(const T* in, int H, int W, int C, int Cvalid, int pad, float* out) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long>(H) * W * Cvalid) return;
   const int c = static_cast<int>(i / (static_cast<long>(H) * W));
   const long pix = i - static_cast<long>(c) * H * W;
-  out[i] = static_cast<float>(in[pix * C + c]);
+  const long y = pix / W, x = pix - y * W;
+  out[i] = static_cast<float>(in[((y + pad) * (W + 2 * pad) + (x + pad)) * C + c]);
 }
 }  // namespace vpb
 
@@ -775,8 +810,8 @@ extern "C" long vp_engine_read_tap(vp_engine* e, const char* name, float* dst, l
   float* d = nullptr;
   VPB_CUDA_OK(cudaMalloc(&d, n * 4));
   const int blocks = static_cast<int>((n + 255) / 256);
-  if (e->dtype == VPB_BF16) tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __nv_bfloat16*>(a.p), a.H, a.W, a.C, Cv, d);
-  else tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __half*>(a.p), a.H, a.W, a.C, Cv, d);
+  if (e->dtype == VPB_BF16) tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __nv_bfloat16*>(a.p), a.H, a.W, a.C, Cv, a.pad, d);
+  else tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __half*>(a.p), a.H, a.W, a.C, Cv, a.pad, d);
   cudaError_t ce = cudaMemcpyAsync(dst, d, n * 4, cudaMemcpyDeviceToHost, e->stream);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
   cudaFree(d);

@@ -7,7 +7,8 @@
 
 namespace vpb {
 
-static constexpr int kNetH = 320, kNetW = 640;  // the only network input size (scene_seg_infer.py:40-42)
+static constexpr int kNetH = 320, kNetW = 640;
+static constexpr int kGapReplicas = 8;           // copies of each SE pooling accumulator (atomic spreading)  // the only network input size (scene_seg_infer.py:40-42)
 
 void resize_tables_host(int mode, int in_size, int out_size, std::vector<int>& bounds,
                         std::vector<int>& coeffs, int& ksize);
@@ -24,6 +25,9 @@ struct PreprocessPlan {
   int configure(int in_h, int in_w, int mode);
   int launch(const uint8_t* src, int stride, int convention, int dtype, void* out, uint8_t* out_u8,
              cudaStream_t stream) const;
+  bool owns_kernel(const void* func, int dtype) const;
+  int update_graph_node(cudaGraphExec_t exec, cudaGraphNode_t node, const uint8_t* src, int stride,
+                        int convention, int dtype, void* out, uint8_t* out_u8) const;
   ~PreprocessPlan();
 };
 

@@ -132,9 +132,9 @@ static constexpr int kMaxPatchBytes = 20480;  // staged input patch bytes per bl
 template <class E>
 __global__ void __launch_bounds__(256) preprocess_pil_kernel(const PreParams p, int rows_cap,
                                                               int patch_w_cap) {
-  extern __shared__ uint8_t sm[];
+  extern __shared__ __align__(16) uint8_t sm[];
   uint8_t* patch = sm;                                              // [rows][patch_w*3]
-  uint8_t* inter = sm + static_cast<size_t>(rows_cap) * patch_w_cap * 3;  // [rows][kTX][3]
+  uint8_t* inter = sm + static_cast<size_t>(rows_cap) * ((patch_w_cap * 3 + 11) & ~3);  // [rows][kTX][3]
   const int ox0 = blockIdx.x * kTX, oy0 = blockIdx.y * kTY;
   const int ox1 = min(ox0 + kTX, p.OW) - 1, oy1 = min(oy0 + kTY, p.OH) - 1;
   // input extents of this tile (bounds are monotone non-decreasing)
@@ -145,10 +145,18 @@ __global__ void __launch_bounds__(256) preprocess_pil_kernel(const PreParams p, 
   int y_hi = 0;
   for (int y = oy0; y <= oy1; ++y) y_hi = max(y_hi, min(p.yb[y] + p.yks, p.h));
   const int rows = y_hi - y_lo, pw = x_hi - x_lo, pwb = pw * 3;
+  const int pitch = (patch_w_cap * 3 + 11) & ~3;   // smem row pitch (bytes), 4-byte aligned
 
-  for (int i = threadIdx.x; i < rows * pwb; i += blockDim.x) {
-    const int r = i / pwb, b = i - r * pwb;
-    patch[r * patch_w_cap * 3 + b] = __ldg(p.src + static_cast<size_t>(y_lo + r) * p.stride + x_lo * 3 + b);
+  // Stage the input patch with aligned 32-bit loads: row r holds the words covering its byte range;
+  // logical byte b of the row lives at patch[r*pitch + mis_r + b], mis_r = (row address) & 3.
+  const uintptr_t base = reinterpret_cast<uintptr_t>(p.src) + static_cast<size_t>(x_lo) * 3;
+  const int wpr = (pwb + 3 + 3) >> 2;              // words per row (worst-case misalignment)
+  for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
+    const int r = i / wpr, wi = i - r * wpr;
+    const uintptr_t a = base + static_cast<size_t>(y_lo + r) * p.stride;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3)) + wi;
+    if (reinterpret_cast<uintptr_t>(wp) < a + pwb)
+      reinterpret_cast<uint32_t*>(patch + r * pitch)[wi] = __ldg(wp);
   }
   __syncthreads();
   // horizontal pass
@@ -161,7 +169,8 @@ __global__ void __launch_bounds__(256) preprocess_pil_kernel(const PreParams p, 
     const int xb = p.xb[ox];
     const int n = min(p.xks, p.w - xb);
     const int* k = p.xk + static_cast<size_t>(ox) * p.xks;
-    const uint8_t* row = patch + r * patch_w_cap * 3 + (xb - x_lo) * 3 + c;
+    const int mis = static_cast<int>((base + static_cast<size_t>(y_lo + r) * p.stride) & 3);
+    const uint8_t* row = patch + r * pitch + mis + (xb - x_lo) * 3 + c;
     int acc = 1 << 21;
     for (int t = 0; t < n; ++t) acc += k[t] * static_cast<int>(row[3 * t]);
     acc >>= 22;
@@ -244,7 +253,7 @@ int PreprocessPlan::configure(int in_h, int in_w, int mode_) {
       for (int x = x0; x < std::min(x0 + kTX, OW); ++x) hi = std::max(hi, std::min(xb[x] + xks, w));
       patch_w_cap = std::max(patch_w_cap, hi - xb[x0]);
     }
-    smem_bytes = static_cast<size_t>(rows_cap) * patch_w_cap * 3 + static_cast<size_t>(rows_cap) * kTX * 3;
+    smem_bytes = static_cast<size_t>(rows_cap) * ((patch_w_cap * 3 + 11) & ~3) + static_cast<size_t>(rows_cap) * kTX * 3;
     if (smem_bytes > 200 * 1024) {
       vpb_set_error("preprocess: %dx%d -> %dx%d needs %zu B of shared memory per tile (input too large)",
                     w, h, OW, OH, smem_bytes);
@@ -268,10 +277,9 @@ PreprocessPlan::~PreprocessPlan() {
   if (d_tables) cudaFree(d_tables);
 }
 
-int PreprocessPlan::launch(const uint8_t* src, int stride, int convention, int dtype, void* out,
-                           uint8_t* out_u8, cudaStream_t stream) const {
-  PreParams p;
-  p.src = src; p.h = h; p.w = w; p.stride = stride; p.mode = mode;
+static void fill_params(const PreprocessPlan& pl, const uint8_t* src, int stride, int convention,
+                        void* out, uint8_t* out_u8, PreParams& p) {
+  p.src = src; p.h = pl.h; p.w = pl.w; p.stride = stride; p.mode = pl.mode;
   // conventions: see include/vp_b200_ops.h
   static const float kMeanRGB[3] = {0.485f, 0.456f, 0.406f}, kStdRGB[3] = {0.229f, 0.224f, 0.225f};
   p.swap_rb = convention == VPB_CONV_BGR_SWAP ? 1 : 0;
@@ -281,18 +289,61 @@ int PreprocessPlan::launch(const uint8_t* src, int stride, int convention, int d
     p.mean[c] = kMeanRGB[s];
     p.stdv[c] = kStdRGB[s];
   }
-  p.xb = d_tables + off_xb; p.xk = d_tables + off_xk; p.xks = xks;
-  p.yb = d_tables + off_yb; p.yk = d_tables + off_yk; p.yks = yks;
-  p.out = out; p.out_u8 = out_u8; p.OH = OH; p.OW = OW;
+  p.xb = pl.d_tables + pl.off_xb; p.xk = pl.d_tables + pl.off_xk; p.xks = pl.xks;
+  p.yb = pl.d_tables + pl.off_yb; p.yk = pl.d_tables + pl.off_yk; p.yks = pl.yks;
+  p.out = out; p.out_u8 = out_u8; p.OH = pl.OH; p.OW = pl.OW;
+}
+
+static const void* kernel_func(int mode, int dtype) {
+  if (mode == VPB_RESIZE_PIL_BICUBIC)
+    return dtype == VPB_BF16 ? reinterpret_cast<const void*>(preprocess_pil_kernel<BF16>)
+                             : reinterpret_cast<const void*>(preprocess_pil_kernel<F16>);
+  return dtype == VPB_BF16 ? reinterpret_cast<const void*>(preprocess_direct_kernel<BF16>)
+                           : reinterpret_cast<const void*>(preprocess_direct_kernel<F16>);
+}
+
+bool PreprocessPlan::owns_kernel(const void* func, int dtype) const { return func == kernel_func(mode, dtype); }
+
+// Re-point the captured pre-process node at another source frame (same geometry): lets the frame
+// graph be replayed on any device buffer without re-capturing.
+int PreprocessPlan::update_graph_node(cudaGraphExec_t exec, cudaGraphNode_t node, const uint8_t* src,
+                                      int stride, int convention, int dtype, void* out,
+                                      uint8_t* out_u8) const {
+  PreParams p;
+  fill_params(*this, src, stride, convention, out, out_u8, p);
+  int rc_ = rows_cap, pw_ = patch_w_cap;
+  void* args[3] = {&p, &rc_, &pw_};
+  cudaKernelNodeParams kp{};
+  kp.func = const_cast<void*>(kernel_func(mode, dtype));
+  kp.kernelParams = args;
+  kp.extra = nullptr;
+  if (mode == VPB_RESIZE_PIL_BICUBIC) {
+    kp.gridDim = dim3((OW + kTX - 1) / kTX, (OH + kTY - 1) / kTY);
+    kp.blockDim = dim3(256);
+    kp.sharedMemBytes = static_cast<unsigned>(smem_bytes);
+  } else {
+    kp.gridDim = dim3((OW + 255) / 256, OH);
+    kp.blockDim = dim3(256);
+    kp.sharedMemBytes = 0;
+  }
+  VPB_CUDA_OK(cudaGraphExecKernelNodeSetParams(exec, node, &kp));
+  return VPB_OK;
+}
+
+int PreprocessPlan::launch(const uint8_t* src, int stride, int convention, int dtype, void* out,
+                           uint8_t* out_u8, cudaStream_t stream) const {
+  PreParams p;
+  fill_params(*this, src, stride, convention, out, out_u8, p);
   if (mode == VPB_RESIZE_PIL_BICUBIC) {
     dim3 grid((OW + kTX - 1) / kTX, (OH + kTY - 1) / kTY);
-    if (dtype == VPB_BF16) {
+    static bool attr_done = false;
+    if (!attr_done) {
       VPB_CUDA_OK(cudaFuncSetAttribute(preprocess_pil_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      preprocess_pil_kernel<BF16><<<grid, 256, smem_bytes, stream>>>(p, rows_cap, patch_w_cap);
-    } else {
       VPB_CUDA_OK(cudaFuncSetAttribute(preprocess_pil_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      preprocess_pil_kernel<F16><<<grid, 256, smem_bytes, stream>>>(p, rows_cap, patch_w_cap);
+      attr_done = true;
     }
+    if (dtype == VPB_BF16) preprocess_pil_kernel<BF16><<<grid, 256, smem_bytes, stream>>>(p, rows_cap, patch_w_cap);
+    else preprocess_pil_kernel<F16><<<grid, 256, smem_bytes, stream>>>(p, rows_cap, patch_w_cap);
   } else {
     dim3 grid((OW + 255) / 256, OH);
     if (dtype == VPB_BF16) preprocess_direct_kernel<BF16><<<grid, 256, 0, stream>>>(p);

@@ -40,6 +40,8 @@ enum {
                              (cuda_visualization_kernels.cu:45-75)                             */
 };
 
+enum { VPB_ALGO_TILE = 0, VPB_ALGO_LINEAR = 1 };
+
 const char* vpb_last_error(void);
 void vpb_set_error(const char* fmt, ...);
 
@@ -68,6 +70,13 @@ typedef struct {
   float* out_f32;
   uint8_t* out_cls;
   int bn; /* 0 = auto */
+  /* Zero-bordered ("padded") image layout: tensor stored as [(H+2)*(W+2)][ld] with a one-pixel zero
+   * border; flags say which of in / out / res use it (out/res dims are those of the OUTPUT image). */
+  int in_pad, out_pad, res_pad;
+  int algo;               /* VPB_ALGO_TILE (default) | VPB_ALGO_LINEAR (3x3 on a padded input:
+                             one TMA segment per kernel row serves the three dx taps) */
+  int dbg_base_offset;    /* experiment hook: also set the descriptor base_offset = dx in the LINEAR
+                             kernel (measured WRONG on B200; default 0 is the correct setting) */
 } vpb_conv_args;
 int vpb_conv_gemm(const vpb_conv_args* a, void* stream);
 
@@ -98,15 +107,16 @@ int vpb_resize_tables_host(int mode, int in_size, int out_size, int* bounds, int
 int vpb_stem_conv(int dtype, const void* in, int H, int W, const float* w, const float* bias,
                   void* out, void* stream);
 /* depthwise k x k (k = 3 or 5), stride 1 or 2, pad (k-1)/2, + bias + SiLU; also accumulates the
- * squeeze-excitation average pool: gap_acc[C] int64, 2^-24 fixed point, must be zero on entry
- * (integer atomics => the pooled sum is bit-reproducible regardless of block order).
+ * squeeze-excitation average pool: gap_acc[8][C] int64 (8 replicas that the SE kernel sums),
+ * 2^-24 fixed point, must be zero on entry (integer atomics => the pooled sum is
+ * bit-reproducible regardless of block order).
  * in [H][W][C] -> out [Ho][Wo][C]; w fp32 [k*k][C]. */
 int vpb_depthwise(int dtype, const void* in, int H, int W, int C, int k, int stride, const float* w,
                   const float* bias, void* out, long long* gap_acc, void* stream);
 /* squeeze-excitation: mean = gap_acc * 2^-24 / HW; s = sigmoid(W2 silu(W1 mean + b1) + b2); then
  * w_scaled[n][k] = w_proj[n][k] * s[k]  (the channel scale is folded into the following 1x1
  * projection's weights instead of re-writing the activation tensor).
- * w1 fp32 [sq][C], w2 fp32 [C][sq], w_proj fp32 [Cout][C] -> w_scaled 16-bit [Cout][C];
+ * w1 fp32 [sq][C], w2 fp32 TRANSPOSED [sq][C], w_proj fp32 [Cout][C] -> w_scaled 16-bit [Cout][C];
  * scale_out (optional) fp32 [C]. */
 int vpb_se_scale(int dtype, const long long* gap_acc, int HW, int C, int sq, const float* w1,
                  const float* b1, const float* w2, const float* b2, const float* w_proj, int Cout,
@@ -119,13 +129,40 @@ int vpb_gap(int dtype, const void* in, int HW, int C, int ld, float* out, void* 
 int vpb_linear(const float* x, const float* w, const float* b, int in_f, int out_f, int act, float* y,
                void* stream);
 /* context_layer_3: Conv3x3 1->128 + GELU on the 10x20 map (scene_context.py:41-47).
- * in fp32 [H][W], w fp32 [Cout][9], out [H][W][Cout] 16-bit */
+ * in fp32 [H][W], w fp32 [Cout][9], out [H][W][Cout] 16-bit (zero-bordered image if out_pad) */
 int vpb_ctx_conv1(int dtype, const float* in, int H, int W, const float* w, const float* b, int Cout,
-                  void* out, void* stream);
+                  void* out, int out_pad, void* stream);
 /* BackboneFeatureFusion (backbone_feature_fusion.py:13-38): 4/3/2/1 x MaxPool2x2 of f0..f3,
  * concatenated with f4 -> [H4][W4][32+24+40+80+1280]. */
 int vpb_fuse_pool_concat(int dtype, const void* f0, const void* f1, const void* f2, const void* f3,
                          const void* f4, int H4, int W4, void* out, void* stream);
+
+/* ---- output side (all device-resident) ---- */
+/* createMaskKernel (cuda_visualization_kernels.cu:13-42; CPU twin run_model_node.cpp:148-172):
+ * raw fp32 NCHW [C][rows][cols] -> uint8: C>1: argmax (strict >, first max wins) == 1 ? 255 : 0;
+ * C==1: v > 0 ? 255 : 0. */
+int vpb_mask255(const float* raw, int channels, int rows, int cols, uint8_t* out, void* stream);
+/* createEgoLanesMaskKernel (cuda_visualization_kernels.cu:45-75): other>right>left -> {2,1,0}, else 255 */
+int vpb_egolanes_ids(const float* raw, int channels, int rows, int cols, uint8_t* out, void* stream);
+/* EgoLanes*Engine::postProcess (production_release/src/inference/tensorrt_engine.cpp:264-305):
+ * out[i] = raw[i] > threshold ? 1.0f : 0.0f over n = 3*H*W values */
+int vpb_lane_masks(const float* raw, int n, float threshold, float* out, void* stream);
+/* resize-back to the source frame size: cv::resize INTER_NEAREST on the uint8 mask
+ * (run_model_node.cpp:177) and INTER_LINEAR on the CV_32FC1 depth map (run_model_node.cpp:96-104) */
+int vpb_resize_nearest_u8(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, void* stream);
+int vpb_resize_linear_f32(const float* src, int sh, int sw, float* dst, int dh, int dw, void* stream);
+/* Lane poly-fit least squares, fp64, one warp per point set (set i = points offsets[i]..offsets[i+1]):
+ * x = c0*y^order + ... (highest power first), order 1..3 ->  coeffs[set][4] (unused slots 0; NaN if the
+ * set has <= order points), yrange[set][2] = (min_y, max_y) (may be NULL).
+ * Replaces LaneFilter::fitPolySimple (production_release/src/lane_filtering/lane_filter.cpp:56-113),
+ * LaneTracker::fitPoly2ndOrder (src/lane_tracking/lane_tracking.cpp:350-404) and fitQuadPoly
+ * (src/path_planning/poly_fit.cpp:36-75). */
+int vpb_polyfit(const float* xs, const float* ys, const int* offsets, int n_sets, int order,
+                double* coeffs, double* yrange, void* stream);
+/* Estimator::update (production_release/src/path_planning/estimator.cpp:24-74) applied to n_meas
+ * measurement vectors in turn (one per camera for the multi-camera fusion of SURVEY.md 8e);
+ * state and each measurement are [14][2] doubles (mean, variance); NaN mean = "no measurement". */
+int vpb_bayes_fuse(double* state, const double* meas, int n_meas, void* stream);
 
 #ifdef __cplusplus
 }

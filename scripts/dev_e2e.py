@@ -74,6 +74,11 @@ def main():
     for p in sorted(prof, key=lambda p: -p["ms"])[:25]:
         tf = p["flops"] / p["ms"] / 1e9 if p["ms"] > 0 else 0
         print(f"  {p['name']:22s} {p['ms'] * 1e3:8.1f} us  {tf:7.1f} TF/s")
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/profile_{model}.txt", "w") as f:
+        for p in prof:
+            tf = p["flops"] / p["ms"] / 1e9 if p["ms"] > 0 else 0
+            f.write(f"{p['name']:24s} {p['ms'] * 1e3:9.1f} us {tf:8.1f} TF/s gemm={int(p['gemm'])}\n")
     enc = sum(p["ms"] for p in prof if "mb" in p["name"] or "stem" in p["name"] or "enc8" in p["name"])
     print(f"encoder total {enc * 1e3:.1f} us; preprocess {prof[0]['ms'] * 1e3:.1f} us")
 

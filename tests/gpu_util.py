@@ -10,11 +10,24 @@ def tdtype(dtype):
     return torch.bfloat16 if dtype == L.VPB_BF16 else torch.float16
 
 
+def pad_img(x):
+    """[H,W,C] -> zero-bordered [(H+2),(W+2),C] (contiguous)."""
+    H, W, C = x.shape
+    o = torch.zeros(H + 2, W + 2, C, device=x.device, dtype=x.dtype)
+    o[1:-1, 1:-1] = x
+    return o.contiguous()
+
+
 def conv_gemm(x_nhwc, w_tnc, bias, *, taps, phases=1, act=L.ACT_NONE, mode=L.EPI_STORE,
               res=None, final_kind=L.FINAL_NONE, cout=None, ldo=None, bn=0, dtype=L.VPB_F16,
-              cin=None):
-    """x_nhwc [H,W,ldi] 16-bit cuda, w_tnc [taps*phases,Cout,Cin] 16-bit cuda, bias fp32 or None."""
+              cin=None, in_pad=0, out_pad=0, res_pad=0, algo=L.ALGO_TILE, set_bo=0):
+    """x_nhwc [H,W,ldi] 16-bit cuda (or zero-bordered [H+2,W+2,ldi] with in_pad=1), w_tnc
+    [taps*phases,Cout,Cin] 16-bit cuda, bias fp32 or None.  With out_pad=1 the returned tensor is the
+    zero-bordered [(Ho+2),(Wo+2),ldo] image (pre-filled with NaN for the LINEAR algorithm, which must
+    write its own border, and with zeros for the TILE algorithm, which only writes the interior)."""
     H, W, ldi = x_nhwc.shape
+    if in_pad:
+        H, W = H - 2, W - 2
     T, Cout, Cin = w_tnc.shape
     assert T == taps * phases
     cin = Cin if cin is None else cin
@@ -27,6 +40,7 @@ def conv_gemm(x_nhwc, w_tnc, bias, *, taps, phases=1, act=L.ACT_NONE, mode=L.EPI
     a.inp, a.w = x_nhwc.data_ptr(), w_tnc.data_ptr()
     a.bias = bias.data_ptr() if bias is not None else None
     a.bn = bn
+    a.in_pad, a.out_pad, a.res_pad, a.algo, a.dbg_base_offset = in_pad, out_pad, res_pad, algo, set_bo
     out = out_f32 = out_cls = None
     if mode == L.EPI_FINAL:
         out_f32 = torch.full((Cout, H, W), float("nan"), device="cuda", dtype=torch.float32)
@@ -34,7 +48,11 @@ def conv_gemm(x_nhwc, w_tnc, bias, *, taps, phases=1, act=L.ACT_NONE, mode=L.EPI
         a.out_f32, a.out_cls = out_f32.data_ptr(), out_cls.data_ptr()
     else:
         ldo = ldo or (Cout + 7) // 8 * 8
-        out = torch.full((Ho, Wo, ldo), float("nan"), device="cuda", dtype=tdtype(dtype))
+        if out_pad:
+            fill = float("nan") if algo == L.ALGO_LINEAR else 0.0
+            out = torch.full((Ho + 2, Wo + 2, ldo), fill, device="cuda", dtype=tdtype(dtype))
+        else:
+            out = torch.full((Ho, Wo, ldo), float("nan"), device="cuda", dtype=tdtype(dtype))
         a.out, a.ldo = out.data_ptr(), ldo
         if res is not None:
             a.res, a.ldr = res.data_ptr(), res.shape[2]
