@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <cstdio>
+#include <cstdlib>
 
 namespace vpb {
 
@@ -243,6 +244,14 @@ __host__ __device__ constexpr uint32_t umma_idesc(int fmt /*0 f16, 1 bf16*/, int
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor is still running; it must not touch the predecessor's
+// outputs before pdl_wait().  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -253,6 +262,27 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+}  // namespace vpb
+
+// Host-side launch helper: every kernel of the frame graph is launched with the PDL attribute so that
+// its launch latency and prologue overlap the tail of its predecessor (VPB_PDL=0 disables).
+namespace vpb {
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VPB_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 }  // namespace vpb
 
 // Host-side error helper (used by the .cu launchers)

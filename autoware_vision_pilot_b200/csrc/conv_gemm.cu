@@ -208,69 +208,81 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  pdl_launch_dependents();   // let the next kernel's prologue overlap this kernel
+  pdl_wait();                // predecessor's outputs (our inputs) are complete and visible from here on
 
   const int kiters = p.taps * p.kchunks;
   const int tiles_per_phase = p.tiles_n * p.tiles_h * p.tiles_w;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ph = tile / tiles_per_phase;
-        int r = tile - ph * tiles_per_phase;
-        const int nt = r % p.tiles_n;
-        r /= p.tiles_n;
-        const int twi = r % p.tiles_w;
-        const int thi = r / p.tiles_w;
-        const int h0 = thi * p.TH, w0 = twi * p.TW, n0 = nt * p.BN;
-        for (int t = 0; t < p.taps; ++t) {
-          const int dy = (p.taps == 9) ? (t / 3 - 1) : 0;
-          const int dx = (p.taps == 9) ? (t % 3 - 1) : 0;
-          const int wsel = (p.phases > 1) ? ph : t;
-          for (int c = 0; c < p.kchunks; ++c) {
-            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+    // The whole warp runs the loop converged and one ELECTed lane issues: that lets the compiler
+    // emit the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) directly instead of the
+    // per-instruction BRA.U.ANY loops it needs inside an `if (lane == 0)` region.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int ph = tile / tiles_per_phase;
+      int r = tile - ph * tiles_per_phase;
+      const int nt = r % p.tiles_n;
+      r /= p.tiles_n;
+      const int twi = r % p.tiles_w;
+      const int thi = r / p.tiles_w;
+      const int h0 = thi * p.TH, w0 = twi * p.TW, n0 = nt * p.BN;
+      for (int t = 0; t < p.taps; ++t) {
+        const int dy = (p.taps == 9) ? (t / 3 - 1) : 0;
+        const int dx = (p.taps == 9) ? (t % 3 - 1) : 0;
+        const int wsel = (p.phases > 1) ? ph : t;
+        for (int c = 0; c < p.kchunks; ++c) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          if (elect_one()) {
             const uint32_t full = smem_u32(&bar_full[stage]);
             const uint32_t sa = smem_base + stage * stage_bytes;
             mbar_arrive_expect_tx(full, stage_bytes);
             tma_load_4d(sa, &mapA, full, c * 64, w0 + dx, h0 + dy, 0);
             tma_load_3d(sa + kATileBytes, &mapB, full, c * 64, n0, wsel);
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(E::kUmmaFmt, 128, p.BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
+    // ------------------------------------------------------------ MMA issuer (converged warp, elected lane)
+    const uint32_t idesc = umma_idesc(E::kUmmaFmt, 128, p.BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * kAccStride;
+      for (int k = 0; k < kiters; ++k) {
+        const int c = k % p.kchunks;
+        const int kvalid = min(64, p.Cin - c * 64);
+        const int ksteps = (kvalid + 15) >> 4;
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kAccStride;
-        for (int k = 0; k < kiters; ++k) {
-          const int c = k % p.kchunks;
-          const int kvalid = min(64, p.Cin - c * 64);
-          const int ksteps = (kvalid + 15) >> 4;
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint64_t adesc = umma_desc_k128(sa);
           const uint64_t bdesc = umma_desc_k128(sa + kATileBytes);
-          for (int kk = 0; kk < ksteps; ++kk) {
-            // +32 B along K inside the 128-B swizzle row == +2 in the encoded start address
-            umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+          // +32 B along K inside the 128-B swizzle row == +2 in the encoded start address
+          if (ksteps == 4) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+          } else {
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&bar_empty[stage]));
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          if (k == kiters - 1) umma_commit(smem_u32(&bar_tfull[as]));
         }
-        umma_commit(smem_u32(&bar_tfull[as]));
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -362,28 +374,49 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
-        const int p0 = mt * 128, n0 = nt * p.BN;
-        for (int c = 0; c < p.kchunks; ++c) {
-          for (int dy = 0; dy < 3; ++dy) {
-            mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1u);
+    // ------------------------------------------------------------ TMA producer (converged warp, elected lane)
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+      const int p0 = mt * 128, n0 = nt * p.BN;
+      for (int c = 0; c < p.kchunks; ++c) {
+        for (int dy = 0; dy < 3; ++dy) {
+          mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1u);
+          if (elect_one()) {
             const uint32_t af = smem_u32(&a_full[sa]);
             mbar_arrive_expect_tx(af, kSegRows * 128);
             // 130 consecutive padded pixels starting one pixel left of the tile in row (dy-1)
             tma_load_2d(smem_base + sa * kSegBytes, &mapA, af, c * 64, p0 + (dy - 1) * p.WP - 1);
-            if (++sa == p.na) { sa = 0; pa ^= 1u; }
+          }
+          __syncwarp();
+          if (++sa == p.na) { sa = 0; pa ^= 1u; }
+          if (p.gb == 3) {
+            // one weight stage = the three dx taps of this kernel row (one barrier handshake
+            // per 12 MMAs instead of per 4)
+            mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1u);
+            if (elect_one()) {
+              const uint32_t bf = smem_u32(&b_full[sb]);
+              mbar_arrive_expect_tx(bf, 3 * b_bytes);
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx)
+                tma_load_3d(b_base + (sb * 3 + dx) * b_bytes, &mapB, bf, c * 64, n0, dy * 3 + dx);
+            }
+            __syncwarp();
+            if (++sb == p.nb) { sb = 0; pb ^= 1u; }
+          } else {
             for (int dx = 0; dx < 3; ++dx) {
               mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1u);
-              const uint32_t bf = smem_u32(&b_full[sb]);
-              mbar_arrive_expect_tx(bf, b_bytes);
-              tma_load_3d(b_base + sb * b_bytes, &mapB, bf, c * 64, n0, dy * 3 + dx);
+              if (elect_one()) {
+                const uint32_t bf = smem_u32(&b_full[sb]);
+                mbar_arrive_expect_tx(bf, b_bytes);
+                tma_load_3d(b_base + sb * b_bytes, &mapB, bf, c * 64, n0, dy * 3 + dx);
+              }
+              __syncwarp();
               if (++sb == p.nb) { sb = 0; pb ^= 1u; }
             }
           }
@@ -391,44 +424,86 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(E::kUmmaFmt, 128, p.BN);
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kAccStride;
-        uint32_t first = 1;
-        for (int c = 0; c < p.kchunks; ++c) {
-          const int kvalid = min(64, p.Cin - c * 64);
-          const int ksteps = (kvalid + 15) >> 4;
-          for (int dy = 0; dy < 3; ++dy) {
-            mbar_wait(smem_u32(&a_full[sa]), pa);
-            const uint32_t seg = smem_base + sa * kSegBytes;
+    // ------------------------------------------------------------ MMA issuer (converged warp, elected lane)
+    const uint32_t idesc = umma_idesc(E::kUmmaFmt, 128, p.BN);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * kAccStride;
+      uint32_t first = 1;
+      for (int c = 0; c < p.kchunks; ++c) {
+        const int kvalid = min(64, p.Cin - c * 64);
+        const int ksteps = (kvalid + 15) >> 4;
+        for (int dy = 0; dy < 3; ++dy) {
+          const bool last = (c == p.kchunks - 1) && (dy == 2);
+          mbar_wait(smem_u32(&a_full[sa]), pa);
+          const uint32_t seg = smem_base + sa * kSegBytes;
+          if (p.gb == 3) {
+            mbar_wait(smem_u32(&b_full[sb]), pb);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                // tap view: same segment, dx pixel rows further in (swizzle phase follows the address)
+                const uint64_t adesc = umma_desc_k128(seg + dx * 128, p.desc_bo ? static_cast<uint32_t>(dx) : 0u);
+                const uint64_t bdesc = umma_desc_k128(b_base + (sb * 3 + dx) * b_bytes);
+                if (ksteps == 4) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
+                    first = 0;
+                  }
+                } else {
+                  for (int kk = 0; kk < ksteps; ++kk) {
+                    umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
+                    first = 0;
+                  }
+                }
+              }
+              umma_commit(smem_u32(&b_empty[sb]));
+              umma_commit(smem_u32(&a_empty[sa]));
+              if (last) umma_commit(smem_u32(&bar_tfull[as]));
+            }
+            __syncwarp();
+            first = 0;
+            if (++sb == p.nb) { sb = 0; pb ^= 1u; }
+          } else {
             for (int dx = 0; dx < 3; ++dx) {
               mbar_wait(smem_u32(&b_full[sb]), pb);
               tc_fence_after();
-              // tap view: same segment, dx pixel rows further in (swizzle phase follows the address)
-              const uint64_t adesc =
-                  umma_desc_k128(seg + dx * 128, p.desc_bo ? static_cast<uint32_t>(dx) : 0u);
-              const uint64_t bdesc = umma_desc_k128(b_base + sb * b_bytes);
-              for (int kk = 0; kk < ksteps; ++kk) {
-                umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
-                first = 0;
+              if (elect_one()) {
+                const uint64_t adesc = umma_desc_k128(seg + dx * 128, p.desc_bo ? static_cast<uint32_t>(dx) : 0u);
+                const uint64_t bdesc = umma_desc_k128(b_base + sb * b_bytes);
+                if (ksteps == 4) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
+                    first = 0;
+                  }
+                } else {
+                  for (int kk = 0; kk < ksteps; ++kk) {
+                    umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
+                    first = 0;
+                  }
+                }
+                umma_commit(smem_u32(&b_empty[sb]));
+                if (dx == 2) {
+                  umma_commit(smem_u32(&a_empty[sa]));
+                  if (last) umma_commit(smem_u32(&bar_tfull[as]));
+                }
               }
-              umma_commit(smem_u32(&b_empty[sb]));
+              __syncwarp();
+              first = 0;
               if (++sb == p.nb) { sb = 0; pb ^= 1u; }
             }
-            umma_commit(smem_u32(&a_empty[sa]));
-            if (++sa == p.na) { sa = 0; pa ^= 1u; }
           }
+          if (++sa == p.na) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(smem_u32(&bar_tfull[as]));
       }
     }
   } else {
@@ -568,10 +643,14 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     p.tiles_m = (p.NP + 127) / 128;
     p.total_tiles = p.tiles_m * p.tiles_n;
     p.na = p.BN >= 256 ? 3 : 4;
+    // weight ring: slots of gb tiles; gb = 3 (a whole kernel row per barrier) when at least 3 such
+    // slots fit, else one tap per slot
+    p.gb = (a->dbg_gb == 1 || p.BN > 144) ? 1 : 3;
     const size_t left = kMaxDynSmem - 1024 - static_cast<size_t>(p.na) * kSegBytes;
-    p.nb = static_cast<int>(std::min<size_t>(kMaxRing, left / b_bytes));
+    const size_t slot = b_bytes * p.gb;
+    p.nb = static_cast<int>(std::min<size_t>(kMaxRing, left / slot));
     if (p.nb < 3) { vpb_set_error("conv: no room for the weight ring"); return VPB_ERR_ARG; }
-    plan->smem_bytes = static_cast<size_t>(p.na) * kSegBytes + p.nb * b_bytes + 1024;
+    plan->smem_bytes = static_cast<size_t>(p.na) * kSegBytes + p.nb * slot + 1024;
     p.TW = 128; p.TH = 1; p.tw_shift = 7;
   } else {
     // spatial tile: minimise padded pixels, prefer wide tiles
@@ -655,14 +734,14 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     attr_set = true;
   }
   const bool bf = plan->dtype == VPB_BF16;
+  const dim3 g(plan->grid), b(kThreads);
   if (plan->p.lin) {
-    if (bf) conv3x3_lin_kernel<BF16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA, plan->mapB, plan->p);
-    else conv3x3_lin_kernel<F16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA, plan->mapB, plan->p);
+    if (bf) VPB_CUDA_OK(launch_k(conv3x3_lin_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
+    else VPB_CUDA_OK(launch_k(conv3x3_lin_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
   } else {
-    if (bf) conv_gemm_kernel<BF16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA, plan->mapB, plan->p);
-    else conv_gemm_kernel<F16><<<plan->grid, kThreads, plan->smem_bytes, stream>>>(plan->mapA, plan->mapB, plan->p);
+    if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
+    else VPB_CUDA_OK(launch_k(conv_gemm_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
   }
-  VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
 }
 

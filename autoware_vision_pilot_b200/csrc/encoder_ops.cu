@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const uint2* __restrict_
                                                          const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          uint4* __restrict__ out, int Ho, int Wo) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sw[27 * 32];
   __shared__ float sb[32];
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
@@ -87,6 +89,8 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict_
                                                          uint4* __restrict__ out, int Ho, int Wo,
                                                          long long* __restrict__ gap_acc, int G, int PPB,
                                                          int pix_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];  // [PPB][C]
   constexpr int PAD = (K - 1) / 2;
   const int cg = threadIdx.x % G, pl = threadIdx.x / G;
@@ -158,6 +162,8 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
                                                         const float* __restrict__ w_proj, int Cout,
                                                         typename E::T* __restrict__ w_scaled,
                                                         float* __restrict__ scale_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* mean = sm;        // [C]
   float* hid = sm + C;     // [sq]
@@ -170,15 +176,24 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int C4 = C >> 2;
+  const int C4 = C >> 2;   // C <= 1152 -> at most 9 float4 per lane per row
   for (int j = warp; j < sq; j += nw) {
     const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j) * C);
     const float4* mr = reinterpret_cast<const float4*>(mean);
+    float4 a[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {   // issue every load of the row before the first use
+      const int c = lane + 32 * k;
+      a[k] = c < C4 ? __ldg(wr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float s = 0.f;
-#pragma unroll 12
-    for (int c = lane; c < C4; c += 32) {
-      const float4 a = __ldg(wr + c), m = mr[c];
-      s = fmaf(a.x, m.x, fmaf(a.y, m.y, fmaf(a.z, m.z, fmaf(a.w, m.w, s))));
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C4) {
+        const float4 m = mr[c];
+        s = fmaf(a[k].x, m.x, fmaf(a[k].y, m.y, fmaf(a[k].z, m.z, fmaf(a[k].w, m.w, s))));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -187,8 +202,13 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = b2[c];
-#pragma unroll 16
-    for (int j = 0; j < sq; ++j) s = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), hid[j], s);
+    for (int j0 = 0; j0 < sq; j0 += 16) {
+      float wv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) wv[j] = (j0 + j < sq) ? __ldg(w2t + static_cast<size_t>(j0 + j) * C + c) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (j0 + j < sq) s = fmaf(wv[j], hid[j0 + j], s);
+    }
     const float g = 1.0f / (1.0f + expf(-s));
     gate[c] = g;
     if (scale_out && blockIdx.x == 0) scale_out[c] = g;
@@ -212,6 +232,8 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
 template <class E>
 __global__ void gap_kernel(const typename E::T* __restrict__ in, int HW, int C, int ld,
                            float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
@@ -224,6 +246,8 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
                                                       const float* __restrict__ w,
                                                       const float* __restrict__ b, int in_f, int out_f,
                                                       int act, float* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (o >= out_f) return;
@@ -246,6 +270,8 @@ template <class E>
 __global__ void ctx_conv1_kernel(const float* __restrict__ in, int H, int W,
                                  const float* __restrict__ w, const float* __restrict__ b, int Cout,
                                  typename E::T* __restrict__ out, int out_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= H * W * Cout) return;
   const int co = idx % Cout, pix = idx / Cout;
@@ -271,6 +297,8 @@ __global__ void __launch_bounds__(256) fuse_pool_kernel(const uint4* __restrict_
                                                          const uint4* __restrict__ f3,
                                                          const uint4* __restrict__ f4, int H4, int W4,
                                                          uint4* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   // channel-group layout of the output pixel: [f0:4 | f1:3 | f2:5 | f3:10 | f4:160] = 182 groups
   constexpr int kGroups = 182;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -322,13 +350,11 @@ extern "C" int vpb_stem_conv(int dtype, const void* in, int H, int W, const floa
   const int Ho = H / 2, Wo = W / 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = Ho * Wo;
+  const dim3 g((n + 127) / 128), b(128);
   if (dtype == VPB_BF16)
-    stem_conv_kernel<BF16><<<(n + 127) / 128, 128, 0, st>>>(static_cast<const uint2*>(in), H, W, w, bias,
-                                                           static_cast<uint4*>(out), Ho, Wo);
+    VPB_CUDA_OK(launch_k(stem_conv_kernel<BF16>, g, b, 0, st, static_cast<const uint2*>(in), H, W, w, bias, static_cast<uint4*>(out), Ho, Wo));
   else
-    stem_conv_kernel<F16><<<(n + 127) / 128, 128, 0, st>>>(static_cast<const uint2*>(in), H, W, w, bias,
-                                                          static_cast<uint4*>(out), Ho, Wo);
-  VPB_CUDA_OK(cudaGetLastError());
+    VPB_CUDA_OK(launch_k(stem_conv_kernel<F16>, g, b, 0, st, static_cast<const uint2*>(in), H, W, w, bias, static_cast<uint4*>(out), Ho, Wo));
   return VPB_OK;
 }
 
@@ -344,13 +370,12 @@ extern "C" int vpb_depthwise(int dtype, const void* in, int H, int W, int C, int
   const size_t smem = static_cast<size_t>(g.PPB) * C * sizeof(float);
   const uint4* i4 = static_cast<const uint4*>(in);
   uint4* o4 = static_cast<uint4*>(out);
-#define DW_LAUNCH(E, K)                                                                          \
-  depthwise_kernel<E, K><<<g.nblocks, g.threads, smem, st>>>(i4, H, W, C, stride, w, bias, o4, g.Ho, \
-                                                             g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block)
+#define DW_LAUNCH(E, K)                                                                              \
+  VPB_CUDA_OK(launch_k(depthwise_kernel<E, K>, dim3(g.nblocks), dim3(g.threads), smem, st, i4, H, W, C, \
+                       stride, w, bias, o4, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block))
   if (dtype == VPB_BF16) { if (k == 3) DW_LAUNCH(BF16, 3); else DW_LAUNCH(BF16, 5); }
   else { if (k == 3) DW_LAUNCH(F16, 3); else DW_LAUNCH(F16, 5); }
 #undef DW_LAUNCH
-  VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
 }
 
@@ -362,30 +387,26 @@ extern "C" int vpb_se_scale(int dtype, const long long* gap_acc, int HW, int C, 
   const size_t smem = (2 * static_cast<size_t>(C) + sq) * sizeof(float);
   const int grid = std::max(1, std::min(48, (Cout * C / 8 + 1023) / 1024));
   if (dtype == VPB_BF16)
-    se_scale_kernel<BF16><<<grid, 512, smem, st>>>(gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
-                                                   w_proj, Cout, static_cast<__nv_bfloat16*>(w_scaled),
-                                                   scale_out);
+    VPB_CUDA_OK(launch_k(se_scale_kernel<BF16>, dim3(grid), dim3(512), smem, st, gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
+                         w_proj, Cout, static_cast<__nv_bfloat16*>(w_scaled), scale_out));
   else
-    se_scale_kernel<F16><<<grid, 512, smem, st>>>(gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
-                                                  w_proj, Cout, static_cast<__half*>(w_scaled), scale_out);
-  VPB_CUDA_OK(cudaGetLastError());
+    VPB_CUDA_OK(launch_k(se_scale_kernel<F16>, dim3(grid), dim3(512), smem, st, gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
+                         w_proj, Cout, static_cast<__half*>(w_scaled), scale_out));
   return VPB_OK;
 }
 
 extern "C" int vpb_gap(int dtype, const void* in, int HW, int C, int ld, float* out, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == VPB_BF16)
-    gap_kernel<BF16><<<(C + 127) / 128, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(in), HW, C, ld, out);
+    VPB_CUDA_OK(launch_k(gap_kernel<BF16>, dim3((C + 127) / 128), dim3(128), 0, st, static_cast<const __nv_bfloat16*>(in), HW, C, ld, out));
   else
-    gap_kernel<F16><<<(C + 127) / 128, 128, 0, st>>>(static_cast<const __half*>(in), HW, C, ld, out);
-  VPB_CUDA_OK(cudaGetLastError());
+    VPB_CUDA_OK(launch_k(gap_kernel<F16>, dim3((C + 127) / 128), dim3(128), 0, st, static_cast<const __half*>(in), HW, C, ld, out));
   return VPB_OK;
 }
 
 extern "C" int vpb_linear(const float* x, const float* w, const float* b, int in_f, int out_f, int act,
                           float* y, void* stream) {
-  linear_kernel<<<(out_f + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, b, in_f, out_f, act, y);
-  VPB_CUDA_OK(cudaGetLastError());
+  VPB_CUDA_OK(launch_k(linear_kernel, dim3((out_f + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), x, w, b, in_f, out_f, act, y));
   return VPB_OK;
 }
 
@@ -394,10 +415,9 @@ extern "C" int vpb_ctx_conv1(int dtype, const float* in, int H, int W, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = H * W * Cout;
   if (dtype == VPB_BF16)
-    ctx_conv1_kernel<BF16><<<(n + 255) / 256, 256, 0, st>>>(in, H, W, w, b, Cout, static_cast<__nv_bfloat16*>(out), out_pad);
+    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<BF16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__nv_bfloat16*>(out), out_pad));
   else
-    ctx_conv1_kernel<F16><<<(n + 255) / 256, 256, 0, st>>>(in, H, W, w, b, Cout, static_cast<__half*>(out), out_pad);
-  VPB_CUDA_OK(cudaGetLastError());
+    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<F16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__half*>(out), out_pad));
   return VPB_OK;
 }
 
@@ -409,9 +429,8 @@ extern "C" int vpb_fuse_pool_concat(int dtype, const void* f0, const void* f1, c
   const int blocks = static_cast<int>((warps * 32 + 255) / 256);
 #define FP_ARGS static_cast<const uint4*>(f0), static_cast<const uint4*>(f1), static_cast<const uint4*>(f2), \
                 static_cast<const uint4*>(f3), static_cast<const uint4*>(f4), H4, W4, static_cast<uint4*>(out)
-  if (dtype == VPB_BF16) fuse_pool_kernel<BF16><<<blocks, 256, 0, st>>>(FP_ARGS);
-  else fuse_pool_kernel<F16><<<blocks, 256, 0, st>>>(FP_ARGS);
+  if (dtype == VPB_BF16) VPB_CUDA_OK(launch_k(fuse_pool_kernel<BF16>, dim3(blocks), dim3(256), 0, st, FP_ARGS));
+  else VPB_CUDA_OK(launch_k(fuse_pool_kernel<F16>, dim3(blocks), dim3(256), 0, st, FP_ARGS));
 #undef FP_ARGS
-  VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
 }

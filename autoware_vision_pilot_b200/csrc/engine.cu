@@ -93,6 +93,7 @@ struct OpRec {
   std::function<int(cudaStream_t)> launch;
   double flops = 0;
   bool gemm = false;
+  int lane = 0;   // execution lane (= index of the model that owns the op); lanes run concurrently
 };
 
 struct ModelOut {
@@ -154,10 +155,25 @@ struct vp_engine {
   struct EncOut { Tens f[5]; };
   std::map<uint64_t, EncOut> enc_cache;
   std::map<uint64_t, Tens> trunk_cache;    // hash(enc)+hash(ctx)+hash(neck) -> neck output
+  // Execution lanes: every model's own ops form a lane that starts after the op producing the
+  // tensor it consumes (pre-process, a shared encoder, or a shared neck).  Lanes are separate
+  // streams forked/joined inside the frame graph, so the latency-bound small kernels of one
+  // network overlap with the other networks.
+  int cur_lane = 0;
+  std::vector<int> lane_dep;               // per lane: producer op index, -1 = the pre-process
+  std::map<uint64_t, int> enc_last_op, trunk_last_op;
+  std::vector<cudaStream_t> lane_streams;  // [lane], lane 0 = the engine stream
+  std::vector<cudaEvent_t> op_events;      // [op], only for ops some lane waits on
+  cudaEvent_t ev_pre = nullptr;
+  std::vector<cudaEvent_t> lane_done;
 
   ~vp_engine() {
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
+    for (size_t i = 1; i < lane_streams.size(); ++i) if (lane_streams[i]) cudaStreamDestroy(lane_streams[i]);
+    for (auto ev : op_events) if (ev) cudaEventDestroy(ev);
+    for (auto ev : lane_done) if (ev) cudaEventDestroy(ev);
+    if (ev_pre) cudaEventDestroy(ev_pre);
     for (void* p : dev_allocs) cudaFree(p);
     for (void* p : host_allocs) cudaFreeHost(p);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -212,13 +228,13 @@ struct vp_engine {
     if (rc != VPB_OK) return rc;
     ConvPlan* pp = plan.get();
     plans.push_back(std::move(plan));
-    OpRec op; op.name = name; op.flops = pp->flops; op.gemm = true;
+    OpRec op; op.name = name; op.flops = pp->flops; op.gemm = true; op.lane = cur_lane;
     op.launch = [pp](cudaStream_t s) { return conv_plan_launch(pp, s); };
     ops.push_back(std::move(op));
     return VPB_OK;
   }
   void add_op(const std::string& name, std::function<int(cudaStream_t)> fn, double flops = 0) {
-    OpRec op; op.name = name; op.launch = std::move(fn); op.flops = flops;
+    OpRec op; op.name = name; op.launch = std::move(fn); op.flops = flops; op.lane = cur_lane;
     ops.push_back(std::move(op));
   }
 };
@@ -516,20 +532,23 @@ static int build_model(vp_engine& e, int idx, int kind, const WeightMap& w) {
   const Prefixes pf = prefixes_for(kind);
   const std::string tag = std::to_string(idx) + "/";
   const uint64_t h_enc = hash_prefix(w, pf.enc);
+  e.cur_lane = idx;
+  int dep = -1;
   vp_engine::EncOut enc;
   auto ie = e.enc_cache.find(h_enc);
-  if (ie != e.enc_cache.end()) { enc = ie->second; ++e.shared_encoders; }
+  if (ie != e.enc_cache.end()) { enc = ie->second; ++e.shared_encoders; dep = e.enc_last_op[h_enc]; }
   else {
     int rc = build_encoder(e, w, pf.enc, tag, enc);
     if (rc) return rc;
     e.enc_cache[h_enc] = enc;
+    e.enc_last_op[h_enc] = static_cast<int>(e.ops.size()) - 1;
   }
   for (int i = 0; i < 5; ++i) e.taps[tag + "f" + std::to_string(i)] = enc.f[i];
   uint64_t h_trunk = h_enc;
   { const uint64_t a = hash_prefix(w, pf.ctx), b = hash_prefix(w, pf.neck); h_trunk = fnv1a(fnv1a(h_trunk, &a, 8), &b, 8); }
   Tens neck;
   auto it = e.trunk_cache.find(h_trunk);
-  if (it != e.trunk_cache.end()) { neck = it->second; ++e.shared_trunks; }
+  if (it != e.trunk_cache.end()) { neck = it->second; ++e.shared_trunks; dep = e.trunk_last_op[h_trunk]; }
   else {
     Tens feat = enc.f[4];
     if (kind == VP_EGO_LANES) {  // BackboneFeatureFusion (backbone_feature_fusion.py:13-38)
@@ -546,7 +565,10 @@ static int build_model(vp_engine& e, int idx, int kind, const WeightMap& w) {
     rc = build_neck(e, w, pf.neck, tag, ctx, enc, &neck);
     if (rc) return rc;
     e.trunk_cache[h_trunk] = neck;
+    e.trunk_last_op[h_trunk] = static_cast<int>(e.ops.size()) - 1;
   }
+  e.lane_dep.resize(idx + 1, -1);
+  e.lane_dep[idx] = dep;
   e.taps[tag + "neck"] = neck;
   ModelOut mo; mo.kind = kind;
   int rc = build_head(e, w, pf.head, tag, kind, neck, enc, mo);
@@ -565,11 +587,55 @@ static int ensure_frame_buffers(vp_engine& e, size_t bytes) {
   return VPB_OK;
 }
 
+static int prepare_lanes(vp_engine& e) {
+  const size_t nl = e.lane_dep.size();
+  if (e.lane_streams.size() == nl) return VPB_OK;
+  e.lane_streams.assign(nl, nullptr);
+  e.lane_done.assign(nl, nullptr);
+  e.lane_streams[0] = e.stream;
+  for (size_t l = 1; l < nl; ++l) {
+    VPB_CUDA_OK(cudaStreamCreateWithFlags(&e.lane_streams[l], cudaStreamNonBlocking));
+    VPB_CUDA_OK(cudaEventCreateWithFlags(&e.lane_done[l], cudaEventDisableTiming));
+  }
+  VPB_CUDA_OK(cudaEventCreateWithFlags(&e.ev_pre, cudaEventDisableTiming));
+  e.op_events.assign(e.ops.size(), nullptr);
+  for (size_t l = 1; l < nl; ++l)
+    if (e.lane_dep[l] >= 0 && !e.op_events[e.lane_dep[l]])
+      VPB_CUDA_OK(cudaEventCreateWithFlags(&e.op_events[e.lane_dep[l]], cudaEventDisableTiming));
+  return VPB_OK;
+}
+
 static int launch_all(vp_engine& e, const uint8_t* src_dev, int stride, cudaStream_t st) {
-  if (e.d_gap) VPB_CUDA_OK(cudaMemsetAsync(e.d_gap, 0, e.gap_used * 8, st));
-  int rc = e.pre.launch(src_dev, stride, e.cfg.convention, e.dtype, e.d_pre, e.d_resized, st);
+  int rc = prepare_lanes(e);
   if (rc) return rc;
-  for (auto& op : e.ops) { rc = op.launch(st); if (rc) return rc; }
+  const size_t nl = e.lane_dep.size();
+  const bool multi = nl > 1 && e.cfg.single_stream == 0;
+  if (e.d_gap) VPB_CUDA_OK(cudaMemsetAsync(e.d_gap, 0, e.gap_used * 8, st));
+  rc = e.pre.launch(src_dev, stride, e.cfg.convention, e.dtype, e.d_pre, e.d_resized, st);
+  if (rc) return rc;
+  if (!multi) {
+    for (auto& op : e.ops) { rc = op.launch(st); if (rc) return rc; }
+    return VPB_OK;
+  }
+  VPB_CUDA_OK(cudaEventRecord(e.ev_pre, st));
+  std::vector<char> started(nl, 0);
+  for (size_t i = 0; i < e.ops.size(); ++i) {
+    auto& op = e.ops[i];
+    cudaStream_t s = op.lane == 0 ? st : e.lane_streams[op.lane];
+    if (op.lane > 0 && !started[op.lane]) {   // fork: wait for the producer of this lane's input
+      const int dep = e.lane_dep[op.lane];
+      VPB_CUDA_OK(cudaStreamWaitEvent(s, dep < 0 ? e.ev_pre : e.op_events[dep], 0));
+      started[op.lane] = 1;
+    }
+    rc = op.launch(s);
+    if (rc) return rc;
+    if (e.op_events[i]) VPB_CUDA_OK(cudaEventRecord(e.op_events[i], s));
+  }
+  for (size_t l = 1; l < nl; ++l) {           // join
+    if (!started[l]) continue;
+    VPB_CUDA_OK(cudaEventRecord(e.lane_done[l], e.lane_streams[l]));
+    VPB_CUDA_OK(cudaStreamWaitEvent(st, e.lane_done[l], 0));
+  }
   return VPB_OK;
 }
 

@@ -132,6 +132,8 @@ static constexpr int kMaxPatchBytes = 20480;  // staged input patch bytes per bl
 template <class E>
 __global__ void __launch_bounds__(256) preprocess_pil_kernel(const PreParams p, int rows_cap,
                                                               int patch_w_cap) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t sm[];
   uint8_t* patch = sm;                                              // [rows][patch_w*3]
   uint8_t* inter = sm + static_cast<size_t>(rows_cap) * ((patch_w_cap * 3 + 11) & ~3);  // [rows][kTX][3]
@@ -200,6 +202,8 @@ __global__ void __launch_bounds__(256) preprocess_pil_kernel(const PreParams p, 
 // OpenCV path (and the no-resize path): one thread per output pixel, gather from global.
 template <class E>
 __global__ void __launch_bounds__(256) preprocess_direct_kernel(const PreParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int oy = blockIdx.y;
   if (ox >= p.OW) return;
@@ -342,14 +346,13 @@ int PreprocessPlan::launch(const uint8_t* src, int stride, int convention, int d
       VPB_CUDA_OK(cudaFuncSetAttribute(preprocess_pil_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_done = true;
     }
-    if (dtype == VPB_BF16) preprocess_pil_kernel<BF16><<<grid, 256, smem_bytes, stream>>>(p, rows_cap, patch_w_cap);
-    else preprocess_pil_kernel<F16><<<grid, 256, smem_bytes, stream>>>(p, rows_cap, patch_w_cap);
+    if (dtype == VPB_BF16) VPB_CUDA_OK(launch_k(preprocess_pil_kernel<BF16>, grid, dim3(256), smem_bytes, stream, p, rows_cap, patch_w_cap));
+    else VPB_CUDA_OK(launch_k(preprocess_pil_kernel<F16>, grid, dim3(256), smem_bytes, stream, p, rows_cap, patch_w_cap));
   } else {
     dim3 grid((OW + 255) / 256, OH);
-    if (dtype == VPB_BF16) preprocess_direct_kernel<BF16><<<grid, 256, 0, stream>>>(p);
-    else preprocess_direct_kernel<F16><<<grid, 256, 0, stream>>>(p);
+    if (dtype == VPB_BF16) VPB_CUDA_OK(launch_k(preprocess_direct_kernel<BF16>, grid, dim3(256), 0, stream, p));
+    else VPB_CUDA_OK(launch_k(preprocess_direct_kernel<F16>, grid, dim3(256), 0, stream, p));
   }
-  VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
 }
 

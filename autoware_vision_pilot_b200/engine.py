@@ -19,7 +19,8 @@ DTYPE_BY_NAME = {"fp16": L.VPB_F16, "bf16": L.VPB_BF16}
 class _Config(C.Structure):
     _fields_ = [("gpu_id", C.c_int), ("dtype", C.c_int), ("resize_mode", C.c_int), ("convention", C.c_int),
                 ("n_models", C.c_int), ("kinds", C.c_int * 4), ("weights", C.c_char_p * 4),
-                ("fetch_raw", C.c_int), ("use_graph", C.c_int), ("stream", C.c_void_p)]
+                ("fetch_raw", C.c_int), ("use_graph", C.c_int), ("stream", C.c_void_p),
+                ("single_stream", C.c_int)]
 
 
 class _Output(C.Structure):
@@ -70,7 +71,7 @@ class Engine:
 
     def __init__(self, kinds: Sequence[int], weights: Sequence[str], *, gpu_id: int = 0, dtype: str = "fp16",
                  resize_mode: int = RESIZE_NONE, convention: int = CONV_RGB, fetch_raw: bool = True,
-                 use_graph: bool = True, stream: Optional[int] = None):
+                 use_graph: bool = True, stream: Optional[int] = None, single_stream: bool = False):
         self._lib = _bind()
         cfg = _Config()
         cfg.gpu_id, cfg.dtype = gpu_id, DTYPE_BY_NAME[dtype]
@@ -81,6 +82,7 @@ class Engine:
             cfg.weights[i] = w.encode("utf-8")
         cfg.fetch_raw, cfg.use_graph = int(fetch_raw), int(use_graph)
         cfg.stream = stream
+        cfg.single_stream = int(single_stream)
         self._h = C.c_void_p()
         L.check(self._lib.vp_engine_create(C.byref(cfg), C.byref(self._h)), "vp_engine_create")
         self.kinds = list(kinds)

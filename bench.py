@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-stream", action="store_true", help="disable the concurrent per-model lanes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -187,7 +188,8 @@ def main():
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         eng = E.Engine(kinds, paths, gpu_id=local_rank, dtype=args.dtype, resize_mode=E.RESIZE_PIL_BICUBIC,
-                       convention=E.CONV_RGB, fetch_raw=False, use_graph=True, stream=stream.cuda_stream)
+                       convention=E.CONV_RGB, fetch_raw=False, use_graph=True, stream=stream.cuda_stream,
+                       single_stream=args.single_stream)
         # camera stream `rank`: frames seeded 1000*rank + f
         host_frames = [synth.synth_frame(synth.stream_seed(rank, f)) for f in range(4)]
         pool = torch.empty((POOL_FRAMES, H_IN, W_IN, 3), dtype=torch.uint8, device="cuda")

@@ -56,6 +56,7 @@ typedef struct {
   int fetch_raw;                    /* 1: vp_engine_infer also copies the raw fp32 tensors to host */
   int use_graph;                    /* 1: replay the frame as one CUDA graph (default), 0: eager */
   void* stream;                     /* optional caller-owned cudaStream_t; NULL = engine creates one */
+  int single_stream;                /* 1: no concurrent per-model lanes inside the frame graph (debug) */
 } vp_engine_config;
 
 typedef struct {

@@ -21,12 +21,19 @@ LAYERS = [  # name, H, W, Cin, Cout, taps, phases
 
 
 def main():
-    bn = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    lin = "lin" in sys.argv
+    args = [a for a in sys.argv[1:] if a != "lin"]
+    bn = int(args[0]) if args else 0
     lib = L.lib()
     rows = []
     tot_t = tot_f = 0.0
     for name, H, W, Cin, Cout, taps, phases in LAYERS:
-        x = torch.randn(H, W, Cin, device="cuda").half()
+        use_lin = lin and taps == 9
+        if use_lin:
+            x = torch.zeros(H + 2, W + 2, Cin, device="cuda").half()
+            x[1:-1, 1:-1] = torch.randn(H, W, Cin, device="cuda").half()
+        else:
+            x = torch.randn(H, W, Cin, device="cuda").half()
         w = (torch.randn(taps * phases, Cout, Cin, device="cuda") * 0.02).half()
         b = torch.randn(Cout, device="cuda")
         a = L.ConvArgs()
@@ -35,6 +42,8 @@ def main():
         a.act = L.ACT_GELU
         a.inp, a.w, a.bias = x.data_ptr(), w.data_ptr(), b.data_ptr()
         a.bn = bn if Cout >= bn else 0
+        if use_lin:
+            a.in_pad, a.algo = 1, L.ALGO_LINEAR
         Ho, Wo = (2 * H, 2 * W) if phases == 4 else (H, W)
         if Cout <= 16:
             of = torch.empty(Cout, H, W, device="cuda")
@@ -42,8 +51,9 @@ def main():
             a.mode, a.final_kind, a.out_f32, a.out_cls = L.EPI_FINAL, L.FINAL_ARGMAX, of.data_ptr(), oc.data_ptr()
         else:
             ldo = (Cout + 7) // 8 * 8
-            o = torch.empty(Ho, Wo, ldo, device="cuda", dtype=torch.half)
-            a.mode, a.out, a.ldo = L.EPI_STORE, o.data_ptr(), ldo
+            pad = 1 if use_lin else 0
+            o = torch.empty(Ho + 2 * pad, Wo + 2 * pad, ldo, device="cuda", dtype=torch.half)
+            a.mode, a.out, a.ldo, a.out_pad = L.EPI_STORE, o.data_ptr(), ldo, pad
         for _ in range(3):
             L.check(lib.vpb_conv_gemm(C.byref(a), None), name)
         torch.cuda.synchronize()
