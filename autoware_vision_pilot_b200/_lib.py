@@ -33,7 +33,7 @@ class ConvArgs(C.Structure):
         ("out_f32", C.c_void_p), ("out_cls", C.c_void_p),
         ("bn", C.c_int),
         ("in_pad", C.c_int), ("out_pad", C.c_int), ("res_pad", C.c_int),
-        ("algo", C.c_int), ("dbg_gb", C.c_int), ("dbg_base_offset", C.c_int),
+        ("algo", C.c_int), ("dbg_ms", C.c_int), ("dbg_gb", C.c_int), ("dbg_base_offset", C.c_int),
     ]
 
 

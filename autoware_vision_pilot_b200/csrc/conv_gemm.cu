@@ -55,6 +55,7 @@ static constexpr int kMaxDynSmem = 227 * 1024 - 4096;
 // linear kernel
 static constexpr int kSegRows = 130;                 // 128 pixels + one halo pixel each side
 static constexpr int kSegBytes = 17 * 1024;          // slot size (130*128 = 16640 B used)
+static constexpr int kSegBytes2 = 33 * 1024;         // slot size with two M sub-tiles (258 rows)
 static constexpr int kMaxRing = 16;
 
 // ------------------------------------------------------------------------------------------------
@@ -351,7 +352,9 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
-  const uint32_t b_base = smem_base + p.na * kSegBytes;
+  const uint32_t seg_bytes = p.ms == 2 ? kSegBytes2 : kSegBytes;
+  const uint32_t b_base = smem_base + p.na * seg_bytes;
+  const int tile_px = 128 * p.ms;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -383,15 +386,19 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
     uint32_t pa = 0, pb = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
-      const int p0 = mt * 128, n0 = nt * p.BN;
+      const int p0 = mt * tile_px, n0 = nt * p.BN;
       for (int c = 0; c < p.kchunks; ++c) {
         for (int dy = 0; dy < 3; ++dy) {
           mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1u);
           if (elect_one()) {
             const uint32_t af = smem_u32(&a_full[sa]);
-            mbar_arrive_expect_tx(af, kSegRows * 128);
-            // 130 consecutive padded pixels starting one pixel left of the tile in row (dy-1)
-            tma_load_2d(smem_base + sa * kSegBytes, &mapA, af, c * 64, p0 + (dy - 1) * p.WP - 1);
+            mbar_arrive_expect_tx(af, kSegRows * 128 * p.ms);
+            // 130 consecutive padded pixels starting one pixel left of the tile in row (dy-1);
+            // with two M sub-tiles a second 130-row box lands 128 rows further (rows 128,129 are
+            // written twice with identical bytes) — TMA boxes are limited to 256 rows.
+            const int r0 = p0 + (dy - 1) * p.WP - 1;
+            tma_load_2d(smem_base + sa * seg_bytes, &mapA, af, c * 64, r0);
+            if (p.ms == 2) tma_load_2d(smem_base + sa * seg_bytes + 128 * 128, &mapA, af, c * 64, r0 + 128);
           }
           __syncwarp();
           if (++sa == p.na) { sa = 0; pa ^= 1u; }
@@ -442,7 +449,7 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
         for (int dy = 0; dy < 3; ++dy) {
           const bool last = (c == p.kchunks - 1) && (dy == 2);
           mbar_wait(smem_u32(&a_full[sa]), pa);
-          const uint32_t seg = smem_base + sa * kSegBytes;
+          const uint32_t seg = smem_base + sa * seg_bytes;
           if (p.gb == 3) {
             mbar_wait(smem_u32(&b_full[sb]), pb);
             tc_fence_after();
@@ -452,18 +459,18 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
                 // tap view: same segment, dx pixel rows further in (swizzle phase follows the address)
                 const uint64_t adesc = umma_desc_k128(seg + dx * 128, p.desc_bo ? static_cast<uint32_t>(dx) : 0u);
                 const uint64_t bdesc = umma_desc_k128(b_base + (sb * 3 + dx) * b_bytes);
-                if (ksteps == 4) {
+                for (int half = 0; half < p.ms; ++half) {
+                  // second M sub-tile: 128 rows (16 KB, encoded +1024) further, its own accumulator
+                  const uint64_t ad = adesc + static_cast<uint64_t>(half) * 1024u;
+                  const uint32_t dt = d_tmem + half * 128;
+                  if (ksteps == 4) {
 #pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {
-                    umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
-                    first = 0;
-                  }
-                } else {
-                  for (int kk = 0; kk < ksteps; ++kk) {
-                    umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
-                    first = 0;
+                    for (int kk = 0; kk < 4; ++kk) umma_f16(dt, ad + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+                  } else {
+                    for (int kk = 0; kk < ksteps; ++kk) umma_f16(dt, ad + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
                   }
                 }
+                first = 0;
               }
               umma_commit(smem_u32(&b_empty[sb]));
               umma_commit(smem_u32(&a_empty[sa]));
@@ -479,16 +486,14 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
               if (elect_one()) {
                 const uint64_t adesc = umma_desc_k128(seg + dx * 128, p.desc_bo ? static_cast<uint32_t>(dx) : 0u);
                 const uint64_t bdesc = umma_desc_k128(b_base + sb * b_bytes);
-                if (ksteps == 4) {
+                for (int half = 0; half < p.ms; ++half) {
+                  const uint64_t ad = adesc + static_cast<uint64_t>(half) * 1024u;
+                  const uint32_t dt = d_tmem + half * 128;
+                  if (ksteps == 4) {
 #pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {
-                    umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
-                    first = 0;
-                  }
-                } else {
-                  for (int kk = 0; kk < ksteps; ++kk) {
-                    umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
-                    first = 0;
+                    for (int kk = 0; kk < 4; ++kk) umma_f16(dt, ad + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+                  } else {
+                    for (int kk = 0; kk < ksteps; ++kk) umma_f16(dt, ad + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
                   }
                 }
                 umma_commit(smem_u32(&b_empty[sb]));
@@ -518,22 +523,23 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
       const uint32_t aphase = (it >> 1) & 1;
       const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
       const int n0 = nt * p.BN;
-      const int pp = mt * 128 + row;          // linear padded pixel index
-      const int y = pp / p.WP, x = pp - y * p.WP;
-      const bool inside = (pp < p.NP) && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
-      EpiPix px;
-      px.ok = inside;
-      px.zero = (pp < p.NP) && !inside && p.out_pad;
-      const size_t upix = static_cast<size_t>(y - 1) * p.W + (x - 1);   // unpadded index (if inside)
-      px.opix = p.out_pad ? static_cast<size_t>(pp) : upix;
-      px.rpix = p.res_pad ? static_cast<size_t>(pp) : upix;
-      px.fpix = upix;
-
       stage_bias(p, s_bias[as], etid, n0);
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
-      epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
+      for (int half = 0; half < p.ms; ++half) {
+        const int pp = mt * tile_px + half * 128 + row;          // linear padded pixel index
+        const int y = pp / p.WP, x = pp - y * p.WP;
+        const bool inside = (pp < p.NP) && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
+        EpiPix px;
+        px.ok = inside;
+        px.zero = (pp < p.NP) && !inside && p.out_pad;
+        const size_t upix = static_cast<size_t>(y - 1) * p.W + (x - 1);   // unpadded index (if inside)
+        px.opix = p.out_pad ? static_cast<size_t>(pp) : upix;
+        px.rpix = p.res_pad ? static_cast<size_t>(pp) : upix;
+        px.fpix = upix;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128;
+        epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
@@ -632,6 +638,18 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
+  if (a->bn <= 0 && a->Cout >= 128) {
+    // small-M layers (context, first neck blocks): trade N-tile width for CTA count so that the
+    // persistent grid covers more of the 148 SMs (weights are re-streamed from L2, activations
+    // are tiny)
+    const long m_tiles = lin ? (static_cast<long>(a->H + 2) * (a->W + 2) + 127) / 128
+                             : (static_cast<long>(a->H) * a->W + 127) / 128 * a->phases;
+    while (p.BN > 64 && m_tiles * ((a->Cout + p.BN - 1) / p.BN) < 96) {
+      const int nb2 = (p.BN / 2 + 15) / 16 * 16;
+      if ((a->Cout + nb2 - 1) / nb2 * nb2 - a->Cout > a->Cout / 8) break;   // too much N padding
+      p.BN = nb2;
+    }
+  }
   if (p.BN % 16 || p.BN > 256 || p.BN < 16) {
     vpb_set_error("conv: bad BN %d", p.BN);
     return VPB_ERR_ARG;
@@ -640,17 +658,23 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.kchunks = (a->Cin + 63) / 64;
   const size_t b_bytes = static_cast<size_t>(p.BN) * 128;
   if (lin) {
-    p.tiles_m = (p.NP + 127) / 128;
+    // two M sub-tiles per CTA (256 pixels, two accumulators sharing every weight tile) when the
+    // accumulators fit twice (BN <= 128) and the layer still gives >= 2 waves of tiles
+    p.ms = 1;
+    if (a->dbg_ms != 1 && p.BN <= 128 && ((p.NP + 255) / 256) * p.tiles_n >= 2 * device_sm_count()) p.ms = 2;
+    if (a->dbg_ms == 2 && p.BN <= 128) p.ms = 2;
+    const size_t seg = p.ms == 2 ? kSegBytes2 : kSegBytes;
+    p.tiles_m = (p.NP + 128 * p.ms - 1) / (128 * p.ms);
     p.total_tiles = p.tiles_m * p.tiles_n;
-    p.na = p.BN >= 256 ? 3 : 4;
-    // weight ring: slots of gb tiles; gb = 3 (a whole kernel row per barrier) when at least 3 such
-    // slots fit, else one tap per slot
+    // weight ring: slots of gb tiles; gb = 3 (a whole kernel row per barrier) for BN <= 144
     p.gb = (a->dbg_gb == 1 || p.BN > 144) ? 1 : 3;
-    const size_t left = kMaxDynSmem - 1024 - static_cast<size_t>(p.na) * kSegBytes;
     const size_t slot = b_bytes * p.gb;
-    p.nb = static_cast<int>(std::min<size_t>(kMaxRing, left / slot));
-    if (p.nb < 3) { vpb_set_error("conv: no room for the weight ring"); return VPB_ERR_ARG; }
-    plan->smem_bytes = static_cast<size_t>(p.na) * kSegBytes + p.nb * slot + 1024;
+    const size_t budget = kMaxDynSmem - 1024;
+    p.na = p.ms == 2 ? 3 : (p.BN >= 256 ? 3 : 4);
+    while (p.na > 2 && static_cast<size_t>(p.na) * seg + 3 * slot > budget) --p.na;
+    p.nb = static_cast<int>(std::min<size_t>(kMaxRing, (budget - static_cast<size_t>(p.na) * seg) / slot));
+    if (p.nb < 2) { vpb_set_error("conv: no room for the weight ring"); return VPB_ERR_ARG; }
+    plan->smem_bytes = static_cast<size_t>(p.na) * seg + p.nb * slot + 1024;
     p.TW = 128; p.TH = 1; p.tw_shift = 7;
   } else {
     // spatial tile: minimise padded pixels, prefer wide tiles

@@ -20,6 +20,7 @@ struct ConvKParams {
   int lin;                       // 1 = linear-padded 3x3 kernel
   int na, nb;                    // linear kernel: activation-segment / weight-slot ring depths
   int gb;                        // linear kernel: weight tiles per slot (3 = one kernel row per barrier)
+  int ms;                        // linear kernel: M sub-tiles (of 128 pixels) per CTA tile, 1 or 2
   int NP, WP, tiles_m;           // linear kernel: padded pixel count, padded width, M tiles
   int in_pad, out_pad, res_pad;  // 1 = that tensor is a zero-bordered image [(H+2)*(W+2)][C]
   int desc_bo;                   // 1 = set the smem-descriptor base_offset for shifted tap views

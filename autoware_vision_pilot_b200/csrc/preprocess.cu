@@ -18,6 +18,7 @@
 // one load.  Optionally also the resized uint8 image (tests compare it bit-exact).
 #include "common.cuh"
 #include "ops_internal.h"
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -139,13 +140,23 @@ __global__ void __launch_bounds__(256) preprocess_pil_kernel(const PreParams p, 
   uint8_t* inter = sm + static_cast<size_t>(rows_cap) * ((patch_w_cap * 3 + 11) & ~3);  // [rows][kTX][3]
   const int ox0 = blockIdx.x * kTX, oy0 = blockIdx.y * kTY;
   const int ox1 = min(ox0 + kTX, p.OW) - 1, oy1 = min(oy0 + kTY, p.OH) - 1;
-  // input extents of this tile (bounds are monotone non-decreasing)
+  // input extents of this tile: the bounds are monotone non-decreasing, so the first / last output
+  // coordinate give the extremes (two loads instead of a dependent chain of 40)
   const int x_lo = p.xb[ox0];
-  int x_hi = 0;
-  for (int x = ox0; x <= ox1; ++x) x_hi = max(x_hi, min(p.xb[x] + p.xks, p.w));
+  const int x_hi = min(p.xb[ox1] + p.xks, p.w);
   const int y_lo = p.yb[oy0];
-  int y_hi = 0;
-  for (int y = oy0; y <= oy1; ++y) y_hi = max(y_hi, min(p.yb[y] + p.yks, p.h));
+  const int y_hi = min(p.yb[oy1] + p.yks, p.h);
+  // this tile's coefficient rows -> shared memory (kTX x-rows, kTY y-rows, <= 32 taps each)
+  __shared__ int s_xk[kTX * 32];
+  __shared__ int s_yk[kTY * 32];
+  for (int i = threadIdx.x; i < kTX * p.xks; i += blockDim.x) {
+    const int xo = i / p.xks, t = i - xo * p.xks;
+    s_xk[xo * 32 + t] = (ox0 + xo < p.OW) ? p.xk[static_cast<size_t>(ox0 + xo) * p.xks + t] : 0;
+  }
+  for (int i = threadIdx.x; i < kTY * p.yks; i += blockDim.x) {
+    const int yo = i / p.yks, t = i - yo * p.yks;
+    s_yk[yo * 32 + t] = (oy0 + yo < p.OH) ? p.yk[static_cast<size_t>(oy0 + yo) * p.yks + t] : 0;
+  }
   const int rows = y_hi - y_lo, pw = x_hi - x_lo, pwb = pw * 3;
   const int pitch = (patch_w_cap * 3 + 11) & ~3;   // smem row pitch (bytes), 4-byte aligned
 
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(256) preprocess_pil_kernel(const PreParams p, 
     const int ox = ox0 + xo;
     const int xb = p.xb[ox];
     const int n = min(p.xks, p.w - xb);
-    const int* k = p.xk + static_cast<size_t>(ox) * p.xks;
+    const int* k = s_xk + xo * 32;
     const int mis = static_cast<int>((base + static_cast<size_t>(y_lo + r) * p.stride) & 3);
     const uint8_t* row = patch + r * pitch + mis + (xb - x_lo) * 3 + c;
     int acc = 1 << 21;
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__(256) preprocess_pil_kernel(const PreParams p, 
     if (ox >= p.OW || oy >= p.OH) continue;
     const int yb = p.yb[oy];
     const int n = min(p.yks, p.h - yb);
-    const int* k = p.yk + static_cast<size_t>(oy) * p.yks;
+    const int* k = s_yk + yo * 32;
     int u[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -243,6 +254,10 @@ int PreprocessPlan::configure(int in_h, int in_w, int mode_) {
   } else {
     resize_tables_host(mode, w, OW, xb, xk, xks);
     resize_tables_host(mode, h, OH, yb, yk, yks);
+  }
+  if (mode == VPB_RESIZE_PIL_BICUBIC && (xks > 32 || yks > 32)) {
+    vpb_set_error("preprocess: %dx%d -> %dx%d needs %d-tap filters (max 32: input at most ~7x the network size)", w, h, OW, OH, std::max(xks, yks));
+    return VPB_ERR_ARG;
   }
   if (mode == VPB_RESIZE_PIL_BICUBIC) {
     // worst-case tile extents for the shared-memory staging

@@ -52,7 +52,7 @@ typedef struct {
   int convention;                   /* VPB_CONV_* */
   int n_models;                     /* 1..VP_MAX_MODELS task heads evaluated per frame */
   int kinds[VP_MAX_MODELS];         /* VP_SCENE_SEG ... */
-  const char* weights[VP_MAX_MODELS]; /* .vpw files (scripts/convert_checkpoint.py from the .pth) */
+  const char* weights[VP_MAX_MODELS]; /* .vpw files (python -m autoware_vision_pilot_b200.convert model.pth) */
   int fetch_raw;                    /* 1: vp_engine_infer also copies the raw fp32 tensors to host */
   int use_graph;                    /* 1: replay the frame as one CUDA graph (default), 0: eager */
   void* stream;                     /* optional caller-owned cudaStream_t; NULL = engine creates one */

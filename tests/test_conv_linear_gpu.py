@@ -127,3 +127,24 @@ def test_tile_kernel_reads_and_writes_padded_images():
     border = u.float().clone()
     border[1:-1, 1:-1] = 0
     assert (border == 0).all()
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout,ms,gb", [
+    (33, 47, 64, 128, 2, 0), (40, 80, 72, 64, 2, 0), (20, 40, 128, 96, 2, 1), (16, 32, 64, 256, 1, 1),
+    (10, 20, 128, 48, 2, 0),
+])
+def test_linear_variants_two_m_subtiles_and_stage_grouping(H, W, Cin, Cout, ms, gb):
+    """Forced kernel variants: 256-pixel CTA tiles with two accumulators sharing each weight tile
+    (ms=2), and one weight tile per pipeline stage instead of a kernel row (gb=1)."""
+    _setup()
+    from tests.gpu_util import conv_gemm, pad_img
+    x, w, b = _mk(H, W, Cin, Cout, seed=H * 3 + Cout)
+    _, _, out = conv_gemm(pad_img(x), w, b, taps=9, act=L.ACT_GELU, in_pad=1, out_pad=1, algo=L.ALGO_LINEAR,
+                          ms=ms, gb=gb)
+    ref = F.gelu(_ref3(x, w, b, Cin)).permute(1, 2, 0)
+    assert torch.isfinite(out.float()).all()
+    err = (out[1:-1, 1:-1, :Cout].float() - ref).abs()
+    assert (err <= 1.5e-3 + 1e-3 * ref.abs()).all(), err.max().item()
+    border = out.float().clone()
+    border[1:-1, 1:-1] = 0
+    assert (border == 0).all()
