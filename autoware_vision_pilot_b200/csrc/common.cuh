@@ -61,24 +61,53 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Exact-erf GELU, branch-free: erfc via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below
-// the 16-bit output rounding), written so that negative inputs have no cancellation:
-//   q = 0.5*|x|*erfc(|x|/sqrt2);  gelu(x) = x - q (x >= 0),  -q (x < 0).
-// ~16 instructions and 2 MUFU ops instead of libdevice erff's ~100 with branches (the first
-// ncu capture showed every layer epilogue-bound on that).
-__device__ __forceinline__ float act_gelu(float x) {
-  const float ax = fabsf(x);
-  const float z = ax * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = ex2_approx(-1.4426950408889634f * z * z);
-  const float q = 0.5f * ax * poly * e;
-  return x >= 0.f ? x - q : -q;
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): two elements per instruction.  The
+// epilogue of the convolution kernels is instruction-issue bound (profiles/r1_conv_v6_ncu.md), so the
+// activation polynomial runs on register pairs.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// Exact-erf GELU, branch-free, on a register pair.
+//   gelu(x) = max(x,0) - q,   q = 0.5*|x|*erfc(|x|/sqrt2)
+// erfc by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the 16-bit output rounding) with the
+// constants pre-folded: t = 1/(1 + (p/sqrt2)|x|), poly' = 0.5*(a1 t + .. + a5 t^5), e = 2^(-x^2 * log2e/2).
+// ~10 instructions per element (2 MUFU) instead of libdevice erff's ~100 with branches — the first ncu
+// capture showed every layer epilogue-bound on that.  No cancellation for negative inputs.
+__device__ __forceinline__ float2 act_gelu2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = ffma2(splat2(0.23164189f), ax, splat2(1.0f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 poly = ffma2(t, splat2(0.5307027145f), splat2(-0.7265760135f));
+  poly = ffma2(poly, t, splat2(0.7107068705f));
+  poly = ffma2(poly, t, splat2(-0.142248368f));
+  poly = ffma2(poly, t, splat2(0.127414796f));
+  poly = fmul2(poly, t);
+  const float2 arg = fmul2(fmul2(x, x), splat2(-0.72134752044f));
+  const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+  const float2 q = fmul2(fmul2(ax, poly), e);
+  return ffma2(q, splat2(-1.0f), make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
+__device__ __forceinline__ float act_gelu(float x) { return act_gelu2(make_float2(x, x)).x; }
 __device__ __forceinline__ float act_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float act_silu(float x) { return x * act_sigmoid(x); }
 __device__ __forceinline__ float apply_act(float x, int act) {

@@ -80,15 +80,23 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_r
     tmem_ld16(t_row + chunk * 16, rr);
     tmem_ld_wait();
     const int n = n0 + chunk * 16;
-    const float* sb = sbias + chunk * 16;
+    const float4* sb4 = reinterpret_cast<const float4*>(sbias + chunk * 16);   // 4 x LDS.128
     float v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + sb[i];
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = sb4[i];
+      const float2 lo = fadd2(make_float2(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1])), make_float2(b4.x, b4.y));
+      const float2 hi = fadd2(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(b4.z, b4.w));
+      v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
+    }
     // activation switch hoisted out of the element loop (act(0) == 0 for GELU/SiLU keeps the
     // channel padding zero; sigmoid is masked explicitly)
     if (p.act == ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = act_gelu(v[i]);
+      for (int i = 0; i < 8; ++i) {   // packed fp32x2: two elements per FFMA2 / FMUL2
+        const float2 g = act_gelu2(make_float2(v[2 * i], v[2 * i + 1]));
+        v[2 * i] = g.x; v[2 * i + 1] = g.y;
+      }
     } else if (p.act == ACT_SILU) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = act_silu(v[i]);
@@ -178,7 +186,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_holder;
-  __shared__ float s_bias[2][256];
+  __shared__ __align__(16) float s_bias[2][256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -346,7 +354,7 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
   __shared__ __align__(8) uint64_t b_full[kMaxRing], b_empty[kMaxRing];
   __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_holder;
-  __shared__ float s_bias[2][256];
+  __shared__ __align__(16) float s_bias[2][256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

@@ -175,40 +175,50 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
     mean[c] = static_cast<float>(static_cast<double>(a) * (1.0 / 16777216.0)) * inv_hw;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C4 = C >> 2;   // C <= 1152 -> at most 9 float4 per lane per row
-  for (int j = warp; j < sq; j += nw) {
-    const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j) * C);
-    const float4* mr = reinterpret_cast<const float4*>(mean);
-    float4 a[9];
+  // FC1: 16 warps x 3 rows cover sq <= 48.  Every global load of all three rows is issued before the
+  // first use (one L2 round trip for the whole phase).
+  {
+    float4 a[3][9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {   // issue every load of the row before the first use
-      const int c = lane + 32 * k;
-      a[k] = c < C4 ? __ldg(wr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < 3; ++r) {
+      const int j = warp + 16 * r;
+      const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j < sq ? j : 0) * C);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int c = lane + 32 * k;
+        a[r][k] = (j < sq && c < C4) ? __ldg(wr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-    float s = 0.f;
+    const float4* mr = reinterpret_cast<const float4*>(mean);
+    float s3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const int c = lane + 32 * k;
-      if (c < C4) {
-        const float4 m = mr[c];
-        s = fmaf(a[k].x, m.x, fmaf(a[k].y, m.y, fmaf(a[k].z, m.z, fmaf(a[k].w, m.w, s))));
-      }
+      const float4 m = c < C4 ? mr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        s3[r] = fmaf(a[r][k].x, m.x, fmaf(a[r][k].y, m.y, fmaf(a[r][k].z, m.z, fmaf(a[r][k].w, m.w, s3[r]))));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) hid[j] = act_silu(s + b1[j]);
+    for (int r = 0; r < 3; ++r) {
+      const int j = warp + 16 * r;
+      float s = s3[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0 && j < sq) hid[j] = act_silu(s + b1[j]);
+    }
   }
   __syncthreads();
+  // FC2 + sigmoid: all (<= 48) weights of a channel in flight at once
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float wv[48];
+#pragma unroll
+    for (int j = 0; j < 48; ++j) wv[j] = j < sq ? __ldg(w2t + static_cast<size_t>(j) * C + c) : 0.f;
     float s = b2[c];
-    for (int j0 = 0; j0 < sq; j0 += 16) {
-      float wv[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) wv[j] = (j0 + j < sq) ? __ldg(w2t + static_cast<size_t>(j0 + j) * C + c) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) if (j0 + j < sq) s = fmaf(wv[j], hid[j0 + j], s);
-    }
+    for (int j = 0; j < 48; ++j) if (j < sq) s = fmaf(wv[j], hid[j], s);
     const float g = 1.0f / (1.0f + expf(-s));
     gate[c] = g;
     if (scale_out && blockIdx.x == 0) scale_out[c] = g;

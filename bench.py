@@ -56,7 +56,8 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one persistent
+    `nvidia-smi -lms 100` child, killed by its own PID afterwards)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -64,28 +65,33 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu: int):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self._halt = gpu, [], threading.Event()
+        self.gpu, self.rows, self.proc = gpu, [], None
 
     def run(self):
-        while not self._halt.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                    "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if line.strip():
+                    self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
 
     def stop(self):
-        self._halt.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
         self.join(timeout=3)
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
 def make_checkpoints(tmpdir: str):
@@ -156,7 +162,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--dtype", default="fp16")

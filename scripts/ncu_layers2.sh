@@ -1,0 +1,13 @@
+#!/bin/bash
+# ncu --set full of the current conv kernels on representative layers (writes gpurun_out/ncu2_*.ncu-rep)
+mkdir -p gpurun_out
+run() {
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:'conv' -s 2 -c 1 -f \
+     -o gpurun_out/ncu2_$1 python scripts/run_layer.py "$@" > gpurun_out/ncu2_$1.log 2>&1
+  tail -1 gpurun_out/ncu2_$1.log
+}
+run dec8 320 640 128 128 9 1 0
+run dec9 320 640 128 64 9 1 0
+run dec6 160 320 256 256 9 1 0
+run up4 160 320 128 128 1 4 0
+run dec0 20 40 1280 768 9 1 0
