@@ -192,7 +192,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_tile_bytes = static_cast<uint32_t>(p.BN) * 128u;
-  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
+  // fuse4 (ConvTranspose): one stage = the A tile + the weight tiles of all four phases, so the
+  // activations are fetched once per K chunk and the four phase accumulators (4 x 128 TMEM
+  // columns) are filled together
+  const int nb_tiles = p.fuse4 ? 4 : 1;
+  const uint32_t stage_bytes = kATileBytes + nb_tiles * b_tile_bytes;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -249,7 +253,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
             const uint32_t sa = smem_base + stage * stage_bytes;
             mbar_arrive_expect_tx(full, stage_bytes);
             tma_load_4d(sa, &mapA, full, c * 64, w0 + dx, h0 + dy, 0);
-            tma_load_3d(sa + kATileBytes, &mapB, full, c * 64, n0, wsel);
+            if (p.fuse4) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                tma_load_3d(sa + kATileBytes + q4 * b_tile_bytes, &mapB, full, c * 64, n0, q4);
+            } else {
+              tma_load_3d(sa + kATileBytes, &mapB, full, c * 64, n0, wsel);
+            }
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -263,8 +273,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      // fuse4 uses all 512 TMEM columns for one tile (single accumulator stage)
+      const int as = p.fuse4 ? 0 : (it & 1);
+      const uint32_t aphase = p.fuse4 ? (it & 1) : ((it >> 1) & 1);
       mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kAccStride;
@@ -277,15 +288,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint64_t adesc = umma_desc_k128(sa);
-          const uint64_t bdesc = umma_desc_k128(sa + kATileBytes);
-          // +32 B along K inside the 128-B swizzle row == +2 in the encoded start address
-          if (ksteps == 4) {
+          for (int q4 = 0; q4 < nb_tiles; ++q4) {
+            const uint64_t bdesc = umma_desc_k128(sa + kATileBytes + q4 * b_tile_bytes);
+            const uint32_t dt = d_tmem + q4 * 128;
+            // +32 B along K inside the 128-B swizzle row == +2 in the encoded start address
+            if (ksteps == 4) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-          } else {
-            for (int kk = 0; kk < ksteps; ++kk)
-              umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16(dt, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            } else {
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_f16(dt, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&bar_empty[stage]));
           if (k == kiters - 1) umma_commit(smem_u32(&bar_tfull[as]));
@@ -305,29 +319,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
     const int Wo = (p.phases > 1) ? 2 * p.W : p.W;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int ph = tile / tiles_per_phase;
-      int r = tile - ph * tiles_per_phase;
+      const int as = p.fuse4 ? 0 : (it & 1);
+      const uint32_t aphase = p.fuse4 ? (it & 1) : ((it >> 1) & 1);
+      const int ph0 = p.fuse4 ? 0 : tile / tiles_per_phase;
+      int r = tile - ph0 * tiles_per_phase;
       const int nt = r % p.tiles_n;
       r /= p.tiles_n;
       const int twi = r % p.tiles_w;
       const int thi = r / p.tiles_w;
       const int h = thi * p.TH + lh, w = twi * p.TW + lw, n0 = nt * p.BN;
-      const int oh = (p.phases > 1) ? 2 * h + (ph >> 1) : h;
-      const int ow = (p.phases > 1) ? 2 * w + (ph & 1) : w;
-      EpiPix px;
-      px.ok = (h < p.H) && (w < p.W);
-      px.zero = false;
-      px.opix = static_cast<size_t>(oh + p.out_pad) * (Wo + 2 * p.out_pad) + (ow + p.out_pad);
-      px.rpix = static_cast<size_t>(oh + p.res_pad) * (Wo + 2 * p.res_pad) + (ow + p.res_pad);
-      px.fpix = static_cast<size_t>(h) * p.W + w;
 
       stage_bias(p, s_bias[as], etid, n0);
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
-      epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
+      for (int q4 = 0; q4 < nb_tiles; ++q4) {
+        const int ph = ph0 + q4;
+        const int oh = (p.phases > 1) ? 2 * h + (ph >> 1) : h;
+        const int ow = (p.phases > 1) ? 2 * w + (ph & 1) : w;
+        EpiPix px;
+        px.ok = (h < p.H) && (w < p.W);
+        px.zero = false;
+        px.opix = static_cast<size_t>(oh + p.out_pad) * (Wo + 2 * p.out_pad) + (ow + p.out_pad);
+        px.rpix = static_cast<size_t>(oh + p.res_pad) * (Wo + 2 * p.res_pad) + (ow + p.res_pad);
+        px.fpix = static_cast<size_t>(h) * p.W + w;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + q4 * 128;
+        epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
@@ -646,7 +663,15 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
-  if (a->bn <= 0 && a->Cout >= 128) {
+  if (a->bn <= 0 && a->phases == 4 && p.BN > 128) {
+    // ConvTranspose runs all four phases per tile (4 accumulators) -> N tile <= 128
+    int best = 128, best_waste = 1 << 30;
+    for (int bn = 128; bn >= 64; bn -= 16) {
+      const int waste = (a->Cout + bn - 1) / bn * bn - a->Cout;
+      if (waste < best_waste) { best_waste = waste; best = bn; }
+    }
+    p.BN = best;
+  } else if (a->bn <= 0 && a->Cout >= 128) {
     // small-M layers (context, first neck blocks): trade N-tile width for CTA count so that the
     // persistent grid covers more of the 148 SMs (weights are re-streamed from L2, activations
     // are tiny)
@@ -696,8 +721,11 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     p.tw_shift = 0; while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
     p.tiles_h = (a->H + p.TH - 1) / p.TH;
     p.tiles_w = (a->W + p.TW - 1) / p.TW;
-    p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * p.phases;
-    const size_t stage_bytes = kATileBytes + b_bytes;
+    // ConvTranspose: all four phases of a pixel tile in one CTA tile (A fetched once per K chunk,
+    // four 128-column accumulators) whenever the N tile is at most 128 wide
+    p.fuse4 = (a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1) ? 1 : 0;
+    p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * (p.fuse4 ? 1 : p.phases);
+    const size_t stage_bytes = kATileBytes + b_bytes * (p.fuse4 ? 4 : 1);
     int stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes);
     p.stages = std::max(2, std::min(stages, kMaxStages));
     plan->smem_bytes = p.stages * stage_bytes + 1024;

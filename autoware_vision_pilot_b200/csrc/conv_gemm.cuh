@@ -18,6 +18,7 @@ struct ConvKParams {
   int kchunks;                   // ceil(Cin / 64)
   int stages;                    // smem pipeline depth (tile kernel)
   int lin;                       // 1 = linear-padded 3x3 kernel
+  int fuse4;                     // tile kernel, ConvTranspose: all 4 phases per CTA tile
   int na, nb;                    // linear kernel: activation-segment / weight-slot ring depths
   int gb;                        // linear kernel: weight tiles per slot (3 = one kernel row per barrier)
   int ms;                        // linear kernel: M sub-tiles (of 128 pixels) per CTA tile, 1 or 2

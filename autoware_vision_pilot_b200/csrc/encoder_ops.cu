@@ -64,6 +64,11 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const uint2* __restrict_
 }
 
 // ------------------------------------------------------------------ depthwise + SiLU + SE pool
+// Register-tiled along x: one thread owns 8 channels of kXT consecutive output pixels, slides the
+// K-wide input window through registers (each activation vector is loaded once per kernel row and
+// each weight vector once per kXT outputs) and does the MACs with packed FFMA2.
+static constexpr int kXT = 4;
+
 DwGeom dw_geometry(int H, int W, int C, int k, int stride) {
   DwGeom g;
   const int pad = (k - 1) / 2;
@@ -72,63 +77,88 @@ DwGeom dw_geometry(int H, int W, int C, int k, int stride) {
   g.G = C / 8;
   g.PPB = std::max(1, 256 / g.G);
   g.threads = g.G * g.PPB;
-  const int npix = g.Ho * g.Wo;
-  // ~2 blocks per SM, each block a contiguous pixel range (multiple of PPB); few blocks keep the
+  const int nitems = g.Ho * ((g.Wo + kXT - 1) / kXT);   // (row, group of kXT columns)
+  // ~2 blocks per SM, each block a contiguous item range (multiple of PPB); few blocks keep the
   // number of pooling atomics (and their contention on a handful of cache lines) low
-  int ppb = (npix + 148 * 2 - 1) / (148 * 2);
+  int ppb = (nitems + 148 * 2 - 1) / (148 * 2);
   ppb = (ppb + g.PPB - 1) / g.PPB * g.PPB;
   g.pix_per_block = std::max(ppb, g.PPB);
-  g.nblocks = (npix + g.pix_per_block - 1) / g.pix_per_block;
+  g.nblocks = (nitems + g.pix_per_block - 1) / g.pix_per_block;
   return g;
 }
 
-template <class E, int K>
+template <class E, int K, int S>
 __global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict__ in, int H, int W,
-                                                         int C, int stride, const float* __restrict__ w,
+                                                         int C, const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          uint4* __restrict__ out, int Ho, int Wo,
                                                          long long* __restrict__ gap_acc, int G, int PPB,
-                                                         int pix_per_block) {
+                                                         int items_per_block) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float red[];  // [PPB][C]
   constexpr int PAD = (K - 1) / 2;
+  constexpr int COLS = (kXT - 1) * S + K;   // input columns feeding kXT outputs
   const int cg = threadIdx.x % G, pl = threadIdx.x / G;
-  const int npix = Ho * Wo;
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(p0 + pix_per_block, npix);
-  float b8[8], sum[8];
+  const int xgroups = (Wo + kXT - 1) / kXT;
+  const int nitems = Ho * xgroups;
+  const int i0 = blockIdx.x * items_per_block;
+  const int i1 = min(i0 + items_per_block, nitems);
+  float2 b2[4];
+  float sum[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { b8[i] = __ldg(bias + cg * 8 + i); sum[i] = 0.f; }
-  for (int pix = p0 + pl; pix < p1; pix += PPB) {
-    const int oy = pix / Wo, ox = pix - oy * Wo;
-    float acc[8];
+  for (int i = 0; i < 4; ++i) b2[i] = make_float2(__ldg(bias + cg * 8 + 2 * i), __ldg(bias + cg * 8 + 2 * i + 1));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = b8[i];
+  for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+  for (int item = i0 + pl; item < i1; item += PPB) {
+    const int oy = item / xgroups, ox0 = (item - oy * xgroups) * kXT;
+    float2 acc[kXT][4];
+#pragma unroll
+    for (int xo = 0; xo < kXT; ++xo)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[xo][i] = b2[i];
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
-      const int iy = oy * stride - PAD + ky;
+      const int iy = oy * S - PAD + ky;
       if (iy < 0 || iy >= H) continue;
+      float2 win[COLS][4];
+#pragma unroll
+      for (int cx = 0; cx < COLS; ++cx) {   // the whole row window in flight before any use
+        const int ix = ox0 * S - PAD + cx;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (ix >= 0 && ix < W) v = __ldg(in + (static_cast<size_t>(iy) * W + ix) * G + cg);
+        win[cx][0] = unpack2<E>(v.x); win[cx][1] = unpack2<E>(v.y);
+        win[cx][2] = unpack2<E>(v.z); win[cx][3] = unpack2<E>(v.w);
+      }
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
-        const int ix = ox * stride - PAD + kx;
-        if (ix < 0 || ix >= W) continue;
-        const uint4 v = __ldg(in + (static_cast<size_t>(iy) * W + ix) * G + cg);
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (ky * K + kx) * C + cg * 8));
         const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (ky * K + kx) * C + cg * 8 + 4));
-        const float2 x0 = unpack2<E>(v.x), x1 = unpack2<E>(v.y), x2 = unpack2<E>(v.z), x3 = unpack2<E>(v.w);
-        acc[0] = fmaf(x0.x, w0.x, acc[0]); acc[1] = fmaf(x0.y, w0.y, acc[1]);
-        acc[2] = fmaf(x1.x, w0.z, acc[2]); acc[3] = fmaf(x1.y, w0.w, acc[3]);
-        acc[4] = fmaf(x2.x, w1.x, acc[4]); acc[5] = fmaf(x2.y, w1.y, acc[5]);
-        acc[6] = fmaf(x3.x, w1.z, acc[6]); acc[7] = fmaf(x3.y, w1.w, acc[7]);
+        const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                              make_float2(w1.z, w1.w)};
+#pragma unroll
+        for (int xo = 0; xo < kXT; ++xo)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[xo][i] = ffma2(win[xo * S + kx][i], wv[i], acc[xo][i]);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i] = act_silu(acc[i]); sum[i] += acc[i]; }
-    uint4 o;
-    o.x = pack2<E>(acc[0], acc[1]); o.y = pack2<E>(acc[2], acc[3]);
-    o.z = pack2<E>(acc[4], acc[5]); o.w = pack2<E>(acc[6], acc[7]);
-    out[static_cast<size_t>(pix) * G + cg] = o;
+    for (int xo = 0; xo < kXT; ++xo) {
+      const int ox = ox0 + xo;
+      if (ox >= Wo) continue;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[2 * i] = act_silu(acc[xo][i].x);
+        v[2 * i + 1] = act_silu(acc[xo][i].y);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum[i] += v[i];
+      uint4 o;
+      o.x = pack2<E>(v[0], v[1]); o.y = pack2<E>(v[2], v[3]);
+      o.z = pack2<E>(v[4], v[5]); o.w = pack2<E>(v[6], v[7]);
+      out[(static_cast<size_t>(oy) * Wo + ox) * G + cg] = o;
+    }
   }
   // SE pooling sums, bit-reproducible: fixed-order reduction inside the block, then ONE 64-bit
   // fixed-point (2^-24) integer atomic per channel — integer addition is order-independent, so
@@ -380,11 +410,18 @@ extern "C" int vpb_depthwise(int dtype, const void* in, int H, int W, int C, int
   const size_t smem = static_cast<size_t>(g.PPB) * C * sizeof(float);
   const uint4* i4 = static_cast<const uint4*>(in);
   uint4* o4 = static_cast<uint4*>(out);
-#define DW_LAUNCH(E, K)                                                                              \
-  VPB_CUDA_OK(launch_k(depthwise_kernel<E, K>, dim3(g.nblocks), dim3(g.threads), smem, st, i4, H, W, C, \
-                       stride, w, bias, o4, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block))
-  if (dtype == VPB_BF16) { if (k == 3) DW_LAUNCH(BF16, 3); else DW_LAUNCH(BF16, 5); }
-  else { if (k == 3) DW_LAUNCH(F16, 3); else DW_LAUNCH(F16, 5); }
+#define DW_LAUNCH(E, K, S)                                                                             \
+  VPB_CUDA_OK(launch_k(depthwise_kernel<E, K, S>, dim3(g.nblocks), dim3(g.threads), smem, st, i4, H, W, C, \
+                       w, bias, o4, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block))
+#define DW_DISPATCH(E)                                            \
+  do {                                                            \
+    if (k == 3 && stride == 1) DW_LAUNCH(E, 3, 1);                \
+    else if (k == 3) DW_LAUNCH(E, 3, 2);                          \
+    else if (stride == 1) DW_LAUNCH(E, 5, 1);                     \
+    else DW_LAUNCH(E, 5, 2);                                      \
+  } while (0)
+  if (dtype == VPB_BF16) DW_DISPATCH(BF16); else DW_DISPATCH(F16);
+#undef DW_DISPATCH
 #undef DW_LAUNCH
   return VPB_OK;
 }

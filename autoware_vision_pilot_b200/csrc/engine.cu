@@ -765,7 +765,17 @@ extern "C" int vp_engine_sync(vp_engine* e) {
   return VPB_OK;
 }
 
+static int submit_host_frame(vp_engine* e, const uint8_t* frame_host, int h, int w, int stride, bool sync);
+
 extern "C" int vp_engine_infer(vp_engine* e, const uint8_t* frame_host, int h, int w, int stride) {
+  return submit_host_frame(e, frame_host, h, w, stride, true);
+}
+
+extern "C" int vp_engine_submit(vp_engine* e, const uint8_t* frame_host, int h, int w, int stride) {
+  return submit_host_frame(e, frame_host, h, w, stride, false);
+}
+
+static int submit_host_frame(vp_engine* e, const uint8_t* frame_host, int h, int w, int stride, bool sync) {
   if (!e || !frame_host || h <= 0 || w <= 0 || stride < w * 3) { vpb_set_error("vp_engine_infer: bad arguments"); return VPB_ERR_ARG; }
   const size_t bytes = static_cast<size_t>(h) * stride;
   int rc = ensure_frame_buffers(*e, bytes);
@@ -779,7 +789,7 @@ extern "C" int vp_engine_infer(vp_engine* e, const uint8_t* frame_host, int h, i
     if (e->cfg.fetch_raw || !mo.has_cls || mo.kind == VP_EGO_LANES)
       VPB_CUDA_OK(cudaMemcpyAsync(mo.h_raw, mo.d_raw, static_cast<size_t>(mo.C) * mo.H * mo.W * 4, cudaMemcpyDeviceToHost, e->stream));
   }
-  VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
+  if (sync) VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
   return VPB_OK;
 }
 

@@ -48,6 +48,7 @@ def _bind():
     lib.vp_engine_destroy.argtypes = [C.c_void_p]
     lib.vp_engine_destroy.restype = None
     lib.vp_engine_infer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.vp_engine_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.vp_engine_infer_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.vp_engine_sync.argtypes = [C.c_void_p]
     lib.vp_engine_fetch_raw.argtypes = [C.c_void_p, C.c_int]
@@ -103,6 +104,11 @@ class Engine:
             frame = np.ascontiguousarray(frame)
         h, w, _ = frame.shape
         L.check(self._lib.vp_engine_infer(self._h, frame.ctypes.data, h, w, frame.strides[0]), "vp_engine_infer")
+
+    def submit(self, frame: np.ndarray) -> None:
+        """Asynchronous infer(): enqueue H2D + kernels + D2H, return at once; sync() completes it."""
+        h, w, _ = frame.shape
+        L.check(self._lib.vp_engine_submit(self._h, frame.ctypes.data, h, w, frame.strides[0]), "vp_engine_submit")
 
     def infer_device(self, dev_ptr: int, h: int, w: int, stride: int) -> None:
         L.check(self._lib.vp_engine_infer_device(self._h, dev_ptr, h, w, stride), "vp_engine_infer_device")

@@ -77,6 +77,11 @@ void vp_engine_destroy(vp_engine* e);
  * results on the host when it returns.  Timed end-to-end this is H2D + kernels + D2H + sync. */
 int vp_engine_infer(vp_engine* e, const uint8_t* frame_host, int h, int w, int stride);
 
+/* Same work as vp_engine_infer (H2D of the host frame, kernels, D2H of the results) but only
+ * ENQUEUED on the engine's stream: returns immediately, vp_engine_sync() completes it.  Use pinned
+ * host frames (vp_engine_pinned_frame); lets one host thread keep several engines / frames in flight. */
+int vp_engine_submit(vp_engine* e, const uint8_t* frame_host, int h, int w, int stride);
+
 /* Asynchronous variants on the engine's stream: frame already resident in device memory, results
  * stay on the device (vp_output.raw_dev / cls_dev); call vp_engine_sync before reading them. */
 int vp_engine_infer_device(vp_engine* e, const uint8_t* frame_dev, int h, int w, int stride);
