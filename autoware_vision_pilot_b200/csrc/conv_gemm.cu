@@ -55,7 +55,8 @@ static constexpr int kMaxDynSmem = 227 * 1024 - 4096;
 // linear kernel
 static constexpr int kSegRows = 130;                 // 128 pixels + one halo pixel each side
 static constexpr int kSegBytes = 17 * 1024;          // slot size (130*128 = 16640 B used)
-static constexpr int kSegBytes2 = 33 * 1024;         // slot size with two M sub-tiles (258 rows)
+// slot size with ms M sub-tiles: (128*ms + 2) rows of 128 B, rounded up to 1 KB
+__host__ __device__ constexpr uint32_t seg_slot_bytes(int ms) { return ((128u * ms + 2u) * 128u + 1023u) & ~1023u; }
 static constexpr int kMaxRing = 16;
 
 // ------------------------------------------------------------------------------------------------
@@ -377,7 +378,8 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
-  const uint32_t seg_bytes = p.ms == 2 ? kSegBytes2 : kSegBytes;
+  const uint32_t seg_bytes = seg_slot_bytes(p.ms);
+  const uint32_t acc_cols = p.BN <= 64 ? 64u : 128u;   // TMEM columns between the M sub-tiles' accumulators
   const uint32_t b_base = smem_base + p.na * seg_bytes;
   const int tile_px = 128 * p.ms;
 
@@ -419,11 +421,11 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
             const uint32_t af = smem_u32(&a_full[sa]);
             mbar_arrive_expect_tx(af, kSegRows * 128 * p.ms);
             // 130 consecutive padded pixels starting one pixel left of the tile in row (dy-1);
-            // with two M sub-tiles a second 130-row box lands 128 rows further (rows 128,129 are
-            // written twice with identical bytes) — TMA boxes are limited to 256 rows.
+            // with several M sub-tiles further 130-row boxes land 128 rows apart (the two overlap
+            // rows are written twice with identical bytes) — TMA boxes are limited to 256 rows.
             const int r0 = p0 + (dy - 1) * p.WP - 1;
-            tma_load_2d(smem_base + sa * seg_bytes, &mapA, af, c * 64, r0);
-            if (p.ms == 2) tma_load_2d(smem_base + sa * seg_bytes + 128 * 128, &mapA, af, c * 64, r0 + 128);
+            for (int j = 0; j < p.ms; ++j)
+              tma_load_2d(smem_base + sa * seg_bytes + j * 128 * 128, &mapA, af, c * 64, r0 + j * 128);
           }
           __syncwarp();
           if (++sa == p.na) { sa = 0; pa ^= 1u; }
@@ -487,7 +489,7 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
                 for (int half = 0; half < p.ms; ++half) {
                   // second M sub-tile: 128 rows (16 KB, encoded +1024) further, its own accumulator
                   const uint64_t ad = adesc + static_cast<uint64_t>(half) * 1024u;
-                  const uint32_t dt = d_tmem + half * 128;
+                  const uint32_t dt = d_tmem + half * acc_cols;
                   if (ksteps == 4) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) umma_f16(dt, ad + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
@@ -513,7 +515,7 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
                 const uint64_t bdesc = umma_desc_k128(b_base + sb * b_bytes);
                 for (int half = 0; half < p.ms; ++half) {
                   const uint64_t ad = adesc + static_cast<uint64_t>(half) * 1024u;
-                  const uint32_t dt = d_tmem + half * 128;
+                  const uint32_t dt = d_tmem + half * acc_cols;
                   if (ksteps == 4) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) umma_f16(dt, ad + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
@@ -562,7 +564,7 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
         px.opix = p.out_pad ? static_cast<size_t>(pp) : upix;
         px.rpix = p.res_pad ? static_cast<size_t>(pp) : upix;
         px.fpix = upix;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * 128;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * acc_cols;
         epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
       }
       tc_fence_before();
@@ -695,15 +697,17 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     // accumulators fit twice (BN <= 128) and the layer still gives >= 2 waves of tiles
     p.ms = 1;
     if (a->dbg_ms != 1 && p.BN <= 128 && ((p.NP + 255) / 256) * p.tiles_n >= 2 * device_sm_count()) p.ms = 2;
+    if (a->dbg_ms != 1 && a->dbg_ms != 2 && p.BN <= 64 && ((p.NP + 511) / 512) * p.tiles_n >= 2 * device_sm_count()) p.ms = 4;
     if (a->dbg_ms == 2 && p.BN <= 128) p.ms = 2;
-    const size_t seg = p.ms == 2 ? kSegBytes2 : kSegBytes;
+    if (a->dbg_ms == 4 && p.BN <= 64) p.ms = 4;
+    const size_t seg = seg_slot_bytes(p.ms);
     p.tiles_m = (p.NP + 128 * p.ms - 1) / (128 * p.ms);
     p.total_tiles = p.tiles_m * p.tiles_n;
     // weight ring: slots of gb tiles; gb = 3 (a whole kernel row per barrier) for BN <= 144
     p.gb = (a->dbg_gb == 1 || p.BN > 144) ? 1 : 3;
     const size_t slot = b_bytes * p.gb;
     const size_t budget = kMaxDynSmem - 1024;
-    p.na = p.ms == 2 ? 3 : (p.BN >= 256 ? 3 : 4);
+    p.na = p.ms >= 2 ? 3 : (p.BN >= 256 ? 3 : 4);
     while (p.na > 2 && static_cast<size_t>(p.na) * seg + 3 * slot > budget) --p.na;
     p.nb = static_cast<int>(std::min<size_t>(kMaxRing, (budget - static_cast<size_t>(p.na) * seg) / slot));
     if (p.nb < 2) { vpb_set_error("conv: no room for the weight ring"); return VPB_ERR_ARG; }
@@ -723,7 +727,10 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     p.tiles_w = (a->W + p.TW - 1) / p.TW;
     // ConvTranspose: all four phases of a pixel tile in one CTA tile (A fetched once per K chunk,
     // four 128-column accumulators) whenever the N tile is at most 128 wide
-    p.fuse4 = (a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1) ? 1 : 0;
+    // ... and only when the fused grid still gives >= 2 waves (measured: with fewer tiles the lost
+    // parallelism and the single-buffered accumulators cost more than the saved A traffic)
+    p.fuse4 = (a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1 &&
+               (p.tiles_h * p.tiles_w * p.tiles_n >= 2 * device_sm_count() || a->dbg_ms == 2)) ? 1 : 0;
     p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * (p.fuse4 ? 1 : p.phases);
     const size_t stage_bytes = kATileBytes + b_bytes * (p.fuse4 ? 4 : 1);
     int stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes);

@@ -55,6 +55,16 @@ def load_peaks():
     return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "src": "fallback"}
 
 
+def load_traffic():
+    """Average DRAM bytes per convolution launch from the committed ncu capture
+    (profiles/r1_conv_traffic.json, produced by scripts/ncu_conv_traffic.sh); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("avg_dram_bytes")
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one persistent
     `nvidia-smi -lms 100` child, killed by its own PID afterwards)."""
@@ -374,7 +384,7 @@ def main():
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      "peak_src": f"{peaks['src']} bf16 cuBLAS, sustained (kernel timed inside a long step)",
                      "launches_timed": n_gemm, "share_of_step": gemm_ms / tot_ms if tot_ms else None,
-                     "traffic": None,
+                     "traffic": load_traffic(),
                      "how": "sum of algorithmic 2*MAC over all conv launches / sum of their CUDA-event durations "
                             f"({prof_runs} eager frames)"},
     }

@@ -131,7 +131,7 @@ def test_tile_kernel_reads_and_writes_padded_images():
 
 @pytest.mark.parametrize("H,W,Cin,Cout,ms,gb", [
     (33, 47, 64, 128, 2, 0), (40, 80, 72, 64, 2, 0), (20, 40, 128, 96, 2, 1), (16, 32, 64, 256, 1, 1),
-    (10, 20, 128, 48, 2, 0),
+    (10, 20, 128, 48, 2, 0), (40, 80, 64, 64, 4, 0), (33, 47, 128, 32, 4, 1), (320, 640, 128, 64, 4, 0),
 ])
 def test_linear_variants_two_m_subtiles_and_stage_grouping(H, W, Cin, Cout, ms, gb):
     """Forced kernel variants: 256-pixel CTA tiles with two accumulators sharing each weight tile
@@ -148,3 +148,23 @@ def test_linear_variants_two_m_subtiles_and_stage_grouping(H, W, Cin, Cout, ms, 
     border = out.float().clone()
     border[1:-1, 1:-1] = 0
     assert (border == 0).all()
+
+
+def test_linearity_at_full_size():
+    """Size-independent property at the real decode_layer_8 size (320x640, 128->128): with no bias
+    and no activation conv(a) + conv(b) == conv(a + b) up to the 16-bit output rounding, and an
+    all-zero input gives exactly zero everywhere (including the written border)."""
+    _setup()
+    from tests.gpu_util import conv_gemm, pad_img
+    g = torch.Generator().manual_seed(11)
+    a = (torch.randn(320, 640, 128, generator=g) * 0.5).half().cuda()
+    b = (torch.randn(320, 640, 128, generator=g) * 0.5).half().cuda()
+    w = (torch.randn(9, 128, 128, generator=g) / 34).half().cuda()
+    ya = conv_gemm(pad_img(a), w, None, taps=9, in_pad=1, out_pad=1, algo=L.ALGO_LINEAR)[2].float()
+    yb = conv_gemm(pad_img(b), w, None, taps=9, in_pad=1, out_pad=1, algo=L.ALGO_LINEAR)[2].float()
+    yab = conv_gemm(pad_img((a.float() + b.float()).half()), w, None, taps=9, in_pad=1, out_pad=1,
+                    algo=L.ALGO_LINEAR)[2].float()
+    assert ((ya + yb - yab).abs() <= 6e-3 + 3e-3 * yab.abs()).all()
+    z = conv_gemm(torch.zeros(322, 642, 128, device="cuda", dtype=torch.half), w, None, taps=9, in_pad=1,
+                  out_pad=1, algo=L.ALGO_LINEAR)[2]
+    assert (z.float() == 0).all()

@@ -238,3 +238,45 @@ def test_cpp_adapters_run_on_gpu(ckpt, tmp_path):
     r = subprocess.run([exe, ckpt["scene_seg"][1], ckpt["ego_lanes"][1]], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "SCENESEG_SHAPE 1 3 320 640" in r.stdout and "EGOLANES_SHAPE 1 3 80 160 mask 80x160" in r.stdout
+
+
+@pytest.mark.parametrize("h,w,mode", [(120, 200, "pil"), (320, 640, "pil"), (90, 1000, "cv"), (4000, 300, "cv")])
+def test_resize_edge_geometries(ckpt, h, w, mode):
+    """Up-scaling, identity and extreme-aspect inputs go through the same integer tables bit-exactly."""
+    f = synth.synth_frame(21, h, w, kind="iid")
+    if mode == "pil":
+        eng = E.Engine([E.EGO_LANES], [ckpt["ego_lanes"][1]], resize_mode=E.RESIZE_PIL_BICUBIC)
+        exp = resize.pil_bicubic_resize(f, 640, 320)
+    else:
+        eng = E.Engine([E.EGO_LANES], [ckpt["ego_lanes"][1]], resize_mode=E.RESIZE_CV_LINEAR)
+        exp = resize.cv_linear_resize(f, 640, 320)
+    eng.infer(f)
+    assert np.array_equal(eng.read_resized(), exp)
+
+
+def test_bad_inputs_are_rejected_not_crashed(ckpt):
+    eng = E.Engine([E.SCENE_SEG], [ckpt["scene_seg"][1]], resize_mode=E.RESIZE_NONE)
+    with pytest.raises(RuntimeError):
+        eng.infer(np.zeros((100, 100, 3), np.uint8))            # resize 'none' needs 640x320
+    with pytest.raises(ValueError):
+        eng.infer(np.zeros((320, 640), np.uint8))               # not HWC
+    big = E.Engine([E.SCENE_SEG], [ckpt["scene_seg"][1]], resize_mode=E.RESIZE_PIL_BICUBIC)
+    with pytest.raises(RuntimeError):
+        big.infer(np.zeros((320 * 9, 640, 3), np.uint8))        # > 32-tap filter: refused with a message
+    with pytest.raises(RuntimeError):
+        E.Engine([E.SCENE_SEG], ["/nonexistent/file.vpw"])
+    with pytest.raises(RuntimeError):
+        E.Engine([E.SCENE_3D], [ckpt["scene_seg"][1]])          # wrong checkpoint for the model kind
+
+
+def test_async_submit_matches_sync_infer(ckpt, frame0):
+    frame, _ = frame0
+    eng = E.Engine([E.SCENE_SEG, E.DOMAIN_SEG], [ckpt["scene_seg"][1], ckpt["domain_seg"][1]],
+                   resize_mode=E.RESIZE_PIL_BICUBIC)
+    eng.infer(frame)
+    a, b = eng.cls(0).copy(), eng.cls(1).copy()
+    pin = eng.pinned_frame(1080, 1920)
+    pin[...] = frame
+    eng.submit(pin)
+    eng.sync()
+    assert np.array_equal(eng.cls(0), a) and np.array_equal(eng.cls(1), b)
