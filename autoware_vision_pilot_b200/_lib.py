@@ -34,6 +34,8 @@ class ConvArgs(C.Structure):
         ("bn", C.c_int),
         ("in_pad", C.c_int), ("out_pad", C.c_int), ("res_pad", C.c_int),
         ("algo", C.c_int), ("dbg_ms", C.c_int), ("dbg_gb", C.c_int), ("dbg_base_offset", C.c_int),
+        ("in2", C.c_void_p), ("w2", C.c_void_p),
+        ("Cin2", C.c_int), ("ld2", C.c_int), ("in2_pad", C.c_int), ("dbg_pair", C.c_int),
     ]
 
 

@@ -180,7 +180,9 @@ __device__ __forceinline__ void stage_bias(const ConvKParams& p, float* dst, int
 template <class E>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
-                 const __grid_constant__ CUtensorMap mapB, const ConvKParams p) {
+                 const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapA2,
+                 const __grid_constant__ CUtensorMap mapB2, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
@@ -202,6 +204,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
+    if (p.kchunks2) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -226,6 +229,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
   pdl_wait();                // predecessor's outputs (our inputs) are complete and visible from here on
 
   const int kiters = p.taps * p.kchunks;
+  const int kiters_all = kiters + p.kchunks2;   // + the fused skip link's K chunks
   const int tiles_per_phase = p.tiles_n * p.tiles_h * p.tiles_w;
 
   if (warp == 0) {
@@ -266,6 +270,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
+      // fused skip link: the same output pixels seen in the second input (at output resolution);
+      // for a ConvTranspose phase (a,b) that is the pixel set (2h+a, 2w+b), addressed through a
+      // 5-D view [h][a][w][b][c] of the tensor so a plain tiled box picks every second pixel
+      for (int c2 = 0; c2 < p.kchunks2; ++c2) {
+        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          mbar_arrive_expect_tx(full, stage_bytes);
+          tma_load_5d(sa, &mapA2, full, c2 * 64, ph & 1, w0, ph >> 1, h0);
+          tma_load_3d(sa + kATileBytes, &mapB2, full, c2 * 64, n0, 0);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (converged warp, elected lane)
@@ -280,9 +299,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
       mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kAccStride;
-      for (int k = 0; k < kiters; ++k) {
+      for (int k = 0; k < kiters_all; ++k) {
         const int c = k % p.kchunks;
-        const int kvalid = min(64, p.Cin - c * 64);
+        const int kvalid = k < kiters ? min(64, p.Cin - c * 64) : min(64, p.Cin2 - (k - kiters) * 64);
         const int ksteps = (kvalid + 15) >> 4;
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
@@ -303,7 +322,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
             }
           }
           umma_commit(smem_u32(&bar_empty[stage]));
-          if (k == kiters - 1) umma_commit(smem_u32(&bar_tfull[as]));
+          if (k == kiters_all - 1) umma_commit(smem_u32(&bar_tfull[as]));
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -581,6 +600,198 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// (3) linear padded formulation on a CTA PAIR (cta_group::2, cluster of two CTAs on one TPC)
+//
+// One pair tile = two adjacent M tiles (CTA rank r owns tile 2*pm + r) x one N tile.  Each CTA stages
+// its own activation segment and HALF of every weight tile (BN/2 rows); the leader issues
+// tcgen05.mma.cta_group::2 with M = 256 and both CTAs' TMEM receive their 128 rows x BN columns.
+// Per SM this halves the weight bytes that have to be staged and read per MMA cycle — the quantity
+// that bounds the 1-CTA kernel (ring depth < TMA round trip at BN = 256, 128 B/clk smem reads at
+// BN = 128) — while pixels, accumulators and the epilogue stay exactly as in conv3x3_lin_kernel.
+//
+// Barriers: full barriers live in the leader and collect the bytes of both CTAs' loads
+// (cp.async.bulk.tensor ... cta_group::2 signals the leader's barrier); empty / accumulator-full
+// barriers exist in both CTAs and are signalled together by one multicast tcgen05.commit; the
+// accumulator-empty barrier lives in the leader and counts the epilogue warps of both CTAs.
+// ------------------------------------------------------------------------------------------------
+template <class E>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA,
+                    const __grid_constant__ CUtensorMap mapB, const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kMaxRing], a_empty[kMaxRing];
+  __shared__ __align__(8) uint64_t b_full[kMaxRing], b_empty[kMaxRing];
+  __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_bias[2][256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bh_bytes = static_cast<uint32_t>(p.BN >> 1) * 128u;   // this CTA's half of a weight tile
+  const uint32_t seg_bytes = seg_slot_bytes(p.ms);
+  const uint32_t acc_cols = p.BN <= 64 ? 64u : 128u;
+  const uint32_t b_base = smem_base + p.na * seg_bytes;
+  const int tile_px = 128 * p.ms;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.na; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 2 * kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(smem_u32(&tmem_holder), 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // peer barriers initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int tile = cid; tile < p.total_tiles; tile += ncl) {
+      const int nt = tile % p.tiles_n, pm = tile / p.tiles_n;
+      const int p0 = (pm * 2 + static_cast<int>(rank)) * tile_px;
+      const int n0 = nt * p.BN + static_cast<int>(rank) * (p.BN >> 1);
+      for (int c = 0; c < p.kchunks; ++c) {
+        for (int dy = 0; dy < 3; ++dy) {
+          mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1u);
+          if (elect_one()) {
+            const uint32_t af = smem_u32(&a_full[sa]) & kPeerBitMask;
+            if (rank == 0) mbar_arrive_expect_tx(af, 2 * kSegRows * 128 * p.ms);
+            const int r0 = p0 + (dy - 1) * p.WP - 1;
+            for (int j = 0; j < p.ms; ++j)
+              tma_load_2d_pair(smem_base + sa * seg_bytes + j * 128 * 128, &mapA, af, c * 64, r0 + j * 128);
+          }
+          __syncwarp();
+          if (++sa == p.na) { sa = 0; pa ^= 1u; }
+          mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1u);
+          if (elect_one()) {
+            const uint32_t bf = smem_u32(&b_full[sb]) & kPeerBitMask;
+            if (rank == 0) mbar_arrive_expect_tx(bf, 2 * 3 * bh_bytes);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_3d_pair(b_base + (sb * 3 + dx) * bh_bytes, &mapB, bf, c * 64, n0, dy * 3 + dx);
+          }
+          __syncwarp();
+          if (++sb == p.nb) { sb = 0; pb ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc(E::kUmmaFmt, 256, p.BN);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = cid; tile < p.total_tiles; tile += ncl, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        uint32_t first = 1;
+        for (int c = 0; c < p.kchunks; ++c) {
+          const int kvalid = min(64, p.Cin - c * 64);
+          const int ksteps = (kvalid + 15) >> 4;
+          for (int dy = 0; dy < 3; ++dy) {
+            const bool last = (c == p.kchunks - 1) && (dy == 2);
+            mbar_wait(smem_u32(&a_full[sa]), pa);
+            mbar_wait(smem_u32(&b_full[sb]), pb);
+            tc_fence_after();
+            const uint32_t seg = smem_base + sa * seg_bytes;
+            if (elect_one()) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint64_t adesc = umma_desc_k128(seg + dx * 128);
+                const uint64_t bdesc = umma_desc_k128(b_base + (sb * 3 + dx) * bh_bytes);
+                for (int half = 0; half < p.ms; ++half) {
+                  const uint64_t ad = adesc + static_cast<uint64_t>(half) * 1024u;
+                  const uint32_t dt = d_tmem + half * acc_cols;
+                  if (ksteps == 4) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_f16_2cta(dt, ad + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+                  } else {
+                    for (int kk = 0; kk < ksteps; ++kk) umma_f16_2cta(dt, ad + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+                  }
+                }
+                first = 0;
+              }
+              umma_commit_pair(smem_u32(&b_empty[sb]));
+              umma_commit_pair(smem_u32(&a_empty[sa]));
+              if (last) umma_commit_pair(smem_u32(&bar_tfull[as]));
+            }
+            __syncwarp();
+            first = 0;
+            if (++sb == p.nb) { sb = 0; pb ^= 1u; }
+            if (++sa == p.na) { sa = 0; pa ^= 1u; }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (both CTAs, own 128 x ms rows)
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = cid; tile < p.total_tiles; tile += ncl, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int nt = tile % p.tiles_n, pm = tile / p.tiles_n;
+      const int mt = pm * 2 + static_cast<int>(rank);
+      const int n0 = nt * p.BN;
+      stage_bias(p, s_bias[as], etid, n0);
+      mbar_wait(smem_u32(&bar_tfull[as]), aphase);
+      tc_fence_after();
+      for (int half = 0; half < p.ms; ++half) {
+        const int pp = mt * tile_px + half * 128 + row;
+        const int y = pp / p.WP, x = pp - y * p.WP;
+        const bool inside = (pp < p.NP) && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
+        EpiPix px;
+        px.ok = inside;
+        px.zero = (pp < p.NP) && !inside && p.out_pad;
+        const size_t upix = static_cast<size_t>(y - 1) * p.W + (x - 1);
+        px.opix = p.out_pad ? static_cast<size_t>(pp) : upix;
+        px.rpix = p.res_pad ? static_cast<size_t>(pp) : upix;
+        px.fpix = upix;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * acc_cols;
+        epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&bar_tempty[as]), 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the leader's MMAs read the peer's shared memory until the very end
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -651,6 +862,13 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
       return VPB_ERR_ARG;
     }
   }
+  if (a->in2) {
+    if (lin || a->taps != 1 || !a->w2 || a->Cin2 <= 0 || (a->Cin2 & 7) || (a->ld2 & 7) || a->ld2 < a->Cin2) {
+      vpb_set_error("conv: second input needs the TILE algorithm, taps=1, w2, Cin2/ld2 multiples of 8 (Cin2=%d ld2=%d)",
+                    a->Cin2, a->ld2);
+      return VPB_ERR_ARG;
+    }
+  }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     vpb_set_error("conv: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -691,6 +909,8 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   }
   p.tiles_n = (a->Cout + p.BN - 1) / p.BN;
   p.kchunks = (a->Cin + 63) / 64;
+  p.Cin2 = a->in2 ? a->Cin2 : 0;
+  p.kchunks2 = (p.Cin2 + 63) / 64;
   const size_t b_bytes = static_cast<size_t>(p.BN) * 128;
   if (lin) {
     // two M sub-tiles per CTA (256 pixels, two accumulators sharing every weight tile) when the
@@ -702,10 +922,15 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     if (a->dbg_ms == 4 && p.BN <= 64) p.ms = 4;
     const size_t seg = seg_slot_bytes(p.ms);
     p.tiles_m = (p.NP + 128 * p.ms - 1) / (128 * p.ms);
-    p.total_tiles = p.tiles_m * p.tiles_n;
-    // weight ring: slots of gb tiles; gb = 3 (a whole kernel row per barrier) for BN <= 144
-    p.gb = (a->dbg_gb == 1 || p.BN > 144) ? 1 : 3;
-    const size_t slot = b_bytes * p.gb;
+    // CTA pair (cta_group::2, M = 256): for the wide layers with at least a wave of tiles — each CTA
+    // then stages only half of every weight tile
+    p.pair = (a->dbg_pair >= 0 && p.BN >= 128 && p.ms <= 2 && p.tiles_m >= 2 &&
+              (a->dbg_pair == 1 || p.tiles_m * p.tiles_n >= device_sm_count())) ? 1 : 0;
+    p.total_tiles = (p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;
+    // weight ring: slots of gb tiles; gb = 3 (a whole kernel row per barrier) whenever three tiles
+    // (half tiles for a pair) stay <= 48 KB
+    p.gb = (p.pair || (a->dbg_gb != 1 && p.BN <= 144)) ? 3 : 1;
+    const size_t slot = (p.pair ? b_bytes / 2 : b_bytes) * p.gb;
     const size_t budget = kMaxDynSmem - 1024;
     p.na = p.ms >= 2 ? 3 : (p.BN >= 256 ? 3 : 4);
     while (p.na > 2 && static_cast<size_t>(p.na) * seg + 3 * slot > budget) --p.na;
@@ -729,7 +954,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     // four 128-column accumulators) whenever the N tile is at most 128 wide
     // ... and only when the fused grid still gives >= 2 waves (measured: with fewer tiles the lost
     // parallelism and the single-buffered accumulators cost more than the saved A traffic)
-    p.fuse4 = (a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1 &&
+    p.fuse4 = (a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1 && !a->in2 &&
                (p.tiles_h * p.tiles_w * p.tiles_n >= 2 * device_sm_count() || a->dbg_ms == 2)) ? 1 : 0;
     p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * (p.fuse4 ? 1 : p.phases);
     const size_t stage_bytes = kATileBytes + b_bytes * (p.fuse4 ? 4 : 1);
@@ -741,8 +966,9 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.bias = a->bias; p.out = a->out; p.ldo = a->ldo; p.res = a->res; p.ldr = a->ldr;
   p.out_f32 = a->out_f32; p.out_cls = a->out_cls;
   plan->dtype = a->dtype;
-  plan->grid = std::min(p.total_tiles, device_sm_count());
-  plan->flops = 2.0 * a->H * a->W * static_cast<double>(a->Cout) * a->Cin * a->taps * a->phases;
+  plan->grid = p.pair ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
+                      : std::min(p.total_tiles, device_sm_count());
+  plan->flops = 2.0 * a->H * a->W * static_cast<double>(a->Cout) * a->phases * (a->Cin * a->taps + p.Cin2);
 
   const CUtensorMapDataType dt =
       a->dtype == VPB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -778,13 +1004,48 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
                           static_cast<cuuint64_t>(a->taps * a->phases)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(a->Cin) * 2,
                              static_cast<cuuint64_t>(a->Cin) * 2 * a->Cout};
-    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(p.BN), 1};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(p.pair ? p.BN / 2 : p.BN), 1};
     cuuint32_t es[3] = {1, 1, 1};
     r = enc(&plan->mapB, dt, 3, const_cast<void*>(a->w), dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       vpb_set_error("conv: cuTensorMapEncodeTiled(B) failed: %d", static_cast<int>(r));
+      return VPB_ERR_CUDA;
+    }
+  }
+  plan->mapA2 = plan->mapA;
+  plan->mapB2 = plan->mapB;
+  if (a->in2) {
+    // second input at output resolution, viewed as [h][a][w][b][c] (s = 2 for a ConvTranspose,
+    // a = b = 0 and s = 1 otherwise); box = one pixel tile of one phase
+    const int s2 = a->phases == 4 ? 2 : 1;
+    const int pad = a->in2_pad ? 1 : 0;
+    const size_t px = static_cast<size_t>(a->ld2) * 2;                       // bytes per pixel
+    const size_t pitch = static_cast<size_t>(a->W * s2 + 2 * pad) * px;      // bytes per image row
+    const uint8_t* base = static_cast<const uint8_t*>(a->in2) + pad * pitch + pad * px;
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(a->Cin2), static_cast<cuuint64_t>(s2),
+                          static_cast<cuuint64_t>(a->W), static_cast<cuuint64_t>(s2),
+                          static_cast<cuuint64_t>(a->H)};
+    cuuint64_t strides[4] = {px, px * s2, pitch, pitch * s2};
+    cuuint32_t box[5] = {64, 1, static_cast<cuuint32_t>(p.TW), 1, static_cast<cuuint32_t>(p.TH)};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    r = enc(&plan->mapA2, dt, 5, const_cast<uint8_t*>(base), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      vpb_set_error("conv: cuTensorMapEncodeTiled(A2) failed: %d", static_cast<int>(r));
+      return VPB_ERR_CUDA;
+    }
+    cuuint64_t bd[3] = {static_cast<cuuint64_t>(a->Cin2), static_cast<cuuint64_t>(a->Cout), 1};
+    cuuint64_t bs[2] = {static_cast<cuuint64_t>(a->Cin2) * 2, static_cast<cuuint64_t>(a->Cin2) * 2 * a->Cout};
+    cuuint32_t bb[3] = {64, static_cast<cuuint32_t>(p.BN), 1};
+    cuuint32_t be[3] = {1, 1, 1};
+    r = enc(&plan->mapB2, dt, 3, const_cast<void*>(a->w2), bd, bs, bb, be,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      vpb_set_error("conv: cuTensorMapEncodeTiled(B2) failed: %d", static_cast<int>(r));
       return VPB_ERR_CUDA;
     }
   }
@@ -798,16 +1059,21 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     VPB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_lin_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_lin_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     attr_set = true;
   }
   const bool bf = plan->dtype == VPB_BF16;
   const dim3 g(plan->grid), b(kThreads);
-  if (plan->p.lin) {
+  if (plan->p.lin && plan->p.pair) {
+    if (bf) VPB_CUDA_OK(launch_k(conv3x3_pair_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
+    else VPB_CUDA_OK(launch_k(conv3x3_pair_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
+  } else if (plan->p.lin) {
     if (bf) VPB_CUDA_OK(launch_k(conv3x3_lin_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
     else VPB_CUDA_OK(launch_k(conv3x3_lin_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
   } else {
-    if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
-    else VPB_CUDA_OK(launch_k(conv_gemm_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
+    if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->mapA2, plan->mapB2, plan->p));
+    else VPB_CUDA_OK(launch_k(conv_gemm_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->mapA2, plan->mapB2, plan->p));
   }
   return VPB_OK;
 }

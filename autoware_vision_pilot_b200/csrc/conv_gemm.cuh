@@ -16,12 +16,14 @@ struct ConvKParams {
   int tiles_h, tiles_w, tiles_n; // tile grid
   int total_tiles;
   int kchunks;                   // ceil(Cin / 64)
+  int Cin2, kchunks2;            // tile kernel: fused second 1x1 input (skip link), 0 = none
   int stages;                    // smem pipeline depth (tile kernel)
   int lin;                       // 1 = linear-padded 3x3 kernel
   int fuse4;                     // tile kernel, ConvTranspose: all 4 phases per CTA tile
   int na, nb;                    // linear kernel: activation-segment / weight-slot ring depths
   int gb;                        // linear kernel: weight tiles per slot (3 = one kernel row per barrier)
-  int ms;                        // linear kernel: M sub-tiles (of 128 pixels) per CTA tile, 1 or 2
+  int ms;                        // linear kernel: M sub-tiles (of 128 pixels) per CTA tile, 1, 2 or 4
+  int pair;                      // linear kernel: 1 = CTA-pair kernel (cta_group::2), tiles are pair tiles
   int NP, WP, tiles_m;           // linear kernel: padded pixel count, padded width, M tiles
   int in_pad, out_pad, res_pad;  // 1 = that tensor is a zero-bordered image [(H+2)*(W+2)][C]
   int desc_bo;                   // 1 = set the smem-descriptor base_offset for shifted tap views
@@ -37,6 +39,7 @@ struct ConvKParams {
 
 struct ConvPlan {
   CUtensorMap mapA, mapB;
+  CUtensorMap mapA2, mapB2;      // second 1x1 input and its weights (copies of mapA/mapB when unused)
   ConvKParams p;
   int dtype;
   int grid;

@@ -212,7 +212,8 @@ struct vp_engine {
   // ---------------------------------------------------------- op emitters
   int add_conv(const std::string& name, const Tens& in, int Cout, int taps, int phases, const void* w,
                const float* bias, int act, int mode, const Tens* out, const Tens* res,
-               int final_kind = 0, float* out_f32 = nullptr, uint8_t* out_cls = nullptr) {
+               int final_kind = 0, float* out_f32 = nullptr, uint8_t* out_cls = nullptr,
+               const Tens* in2 = nullptr, const void* w2 = nullptr) {
     vpb_conv_args a{};
     a.dtype = dtype; a.H = in.H; a.W = in.W; a.Cin = in.C; a.ldi = in.C;
     a.Cout = Cout; a.taps = taps; a.phases = phases; a.act = act; a.mode = mode;
@@ -223,6 +224,7 @@ struct vp_engine {
     // 3x3 on a zero-bordered input -> linear-padded kernel (one TMA segment per kernel row)
     a.algo = (taps == 9 && in.pad) ? VPB_ALGO_LINEAR : VPB_ALGO_TILE;
     a.out_f32 = out_f32; a.out_cls = out_cls;
+    if (in2) { a.in2 = in2->p; a.w2 = w2; a.Cin2 = in2->C; a.ld2 = in2->C; a.in2_pad = in2->pad; }
     auto plan = std::make_unique<ConvPlan>();
     int rc = conv_plan_build(&a, plan.get());
     if (rc != VPB_OK) return rc;
@@ -412,15 +414,25 @@ static int up_skip(vp_engine& e, const WeightMap& w, const std::string& p, int i
   if (!ut || !ub) return VPB_ERR_IO;
   const int Cout = ut->dims[1];
   *out = e.act_alloc(in.H * 2, in.W * 2, Cout, /*pad=*/1);
-  if (skip) {
-    int rc = conv_layer(e, w, p + "skip_link_layer_" + std::to_string(i), tag + "skip" + std::to_string(i), *skip, 1,
-                        ACT_NONE, VPB_EPI_STORE, out, nullptr);
-    if (rc) return rc;
-  }
   void* dw_ = e.upload_16(pack_convT(*ut));
-  float* db = e.upload_f32(ub->f);
-  return e.add_conv(tag + "up" + std::to_string(i), in, Cout, 1, 4, dw_, db, ACT_NONE,
-                    skip ? VPB_EPI_ADD : VPB_EPI_STORE, out, skip ? out : nullptr);
+  if (!skip)
+    return e.add_conv(tag + "up" + std::to_string(i), in, Cout, 1, 4, dw_, e.upload_f32(ub->f), ACT_NONE,
+                      VPB_EPI_STORE, out, nullptr);
+  // the skip link's 1x1 conv is a second K segment of the same GEMM: both layers accumulate in the
+  // fp32 TMEM accumulator and the sum is rounded and written once (no intermediate tensor)
+  const std::string sk = p + "skip_link_layer_" + std::to_string(i);
+  const HostTensor *st = find_w(w, sk + ".weight"), *sb = find_w(w, sk + ".bias");
+  if (!st || !sb) return VPB_ERR_IO;
+  if (st->dims[0] != Cout || st->dims[1] != skip->C || (skip->C & 7)) {
+    vpb_set_error("%s: skip link [%d,%d] does not match Cout=%d / skip channels %d", sk.c_str(), st->dims[0],
+                  st->dims[1], Cout, skip->C);
+    return VPB_ERR_ARG;
+  }
+  void* dw2 = e.upload_16(pack_conv(*st, nullptr));
+  std::vector<float> bsum(ub->f);
+  for (int c = 0; c < Cout; ++c) bsum[c] += sb->f[c];
+  return e.add_conv(tag + "up" + std::to_string(i), in, Cout, 1, 4, dw_, e.upload_f32(bsum), ACT_NONE,
+                    VPB_EPI_STORE, out, nullptr, 0, nullptr, nullptr, skip, dw2);
 }
 
 // SceneContext / DepthContext / AutoSteerContext (scene_context.py:25-57)

@@ -79,6 +79,16 @@ typedef struct {
   int dbg_gb;             /* experiment hook: 1 = one weight tile per pipeline stage in the LINEAR kernel */
   int dbg_base_offset;    /* experiment hook: also set the descriptor base_offset = dx in the LINEAR
                              kernel (measured WRONG on B200; default 0 is the correct setting) */
+  /* Optional second 1x1 input accumulated into the same fp32 accumulator before the epilogue
+   * (TILE algorithm, taps == 1): the neck's skip link  out = ConvT(in) + Conv1x1(in2)
+   * (scene_neck.py:30-32) in ONE pass — in2 lives at the OUTPUT resolution [Ho][Wo][ld2]
+   * (zero-bordered when in2_pad), w2 is [Cout][Cin2] 16-bit, Cin2 and ld2 multiples of 8;
+   * bias must already hold the sum of both layers' biases.  in2 == NULL: disabled. */
+  const void* in2;
+  const void* w2;
+  int Cin2, ld2, in2_pad;
+  int dbg_pair;           /* experiment hook, LINEAR kernel: 1 = force the CTA-pair (cta_group::2) kernel,
+                             -1 = never use it, 0 = auto */
 } vpb_conv_args;
 int vpb_conv_gemm(const vpb_conv_args* a, void* stream);
 

@@ -18,6 +18,7 @@ LAYERS = [  # name, H, W, Cin, Cout, taps, phases
     ("up4", 160, 320, 128, 128, 1, 4), ("dec8", 320, 640, 128, 128, 9, 1), ("dec9", 320, 640, 128, 64, 9, 1),
     ("dec10", 320, 640, 64, 3, 9, 1),
 ]
+SKIP_C = {"up0": 112, "up1": 40, "up2": 24, "up3": 16}   # fused skip-link inputs (encoder taps f3..f0)
 
 
 def main():
@@ -39,7 +40,12 @@ def main():
         a = L.ConvArgs()
         a.dtype = L.VPB_F16
         a.H, a.W, a.Cin, a.ldi, a.Cout, a.taps, a.phases = H, W, Cin, Cin, Cout, taps, phases
-        a.act = L.ACT_GELU
+        a.act = L.ACT_GELU if taps == 9 else L.ACT_NONE
+        c2 = SKIP_C.get(name, 0)
+        if c2:
+            x2 = torch.randn(2 * H, 2 * W, c2, device="cuda").half()
+            w2 = (torch.randn(Cout, c2, device="cuda") * 0.02).half()
+            a.in2, a.w2, a.Cin2, a.ld2 = x2.data_ptr(), w2.data_ptr(), c2, c2
         a.inp, a.w, a.bias = x.data_ptr(), w.data_ptr(), b.data_ptr()
         a.bn = bn if Cout >= bn else 0
         if use_lin:
@@ -65,7 +71,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        fl = 2.0 * H * W * Cout * Cin * taps * phases
+        fl = 2.0 * H * W * Cout * phases * (Cin * taps + c2)
         rows.append({"layer": name, "ms": round(ms, 4), "gflop": round(fl / 1e9, 3), "tflops": round(fl / ms / 1e9, 1)})
         tot_t += ms
         tot_f += fl

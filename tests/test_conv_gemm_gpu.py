@@ -125,6 +125,53 @@ def test_conv_transpose_phases(H, W, Cin, Cout):
     assert (err <= 2e-3 + 1e-3 * ref.abs()).all(), err.max().item()
 
 
+@pytest.mark.parametrize("H,W,Cin,Cout,C2,pad2,out_pad", [
+    (10, 20, 128, 128, 112, 0, 1),     # neck block 0 shape class: skip = f3 (112 ch, K tail 64+48)
+    (20, 40, 96, 72, 40, 0, 0),        # K tails on both inputs, N tail
+    (40, 80, 64, 256, 24, 1, 1),       # zero-bordered skip tensor
+    (80, 160, 256, 256, 16, 0, 1),     # up3 of the SceneSeg head at full size (skip = f0, 16 ch)
+])
+def test_conv_transpose_with_fused_skip_link(H, W, Cin, Cout, C2, pad2, out_pad):
+    """out = ConvTranspose2d(in) + Conv1x1(skip) in one kernel (scene_neck.py:30-32): the skip link is a
+    second K segment read at the output resolution through the 5-D phase view."""
+    _setup()
+    from tests.gpu_util import conv_gemm, pad_img
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(H, W, Cin, generator=g).half().cuda()
+    wt = (torch.randn(Cin, Cout, 2, 2, generator=g) / Cin ** 0.5).half().cuda()
+    skip = torch.randn(2 * H, 2 * W, C2, generator=g).half().cuda()
+    w2 = (torch.randn(Cout, C2, generator=g) / C2 ** 0.5).half().cuda()
+    b = torch.randn(Cout, generator=g).cuda()      # already the sum of both layers' biases
+    w_pnc = wt.permute(2, 3, 1, 0).reshape(4, Cout, Cin).contiguous()
+    in2 = pad_img(skip) if pad2 else skip
+    _, _, out = conv_gemm(x, w_pnc, b, taps=1, phases=4, in2=in2, w2=w2, in2_pad=pad2, out_pad=out_pad)
+    if out_pad:
+        assert (out[0] == 0).all() and (out[-1] == 0).all() and (out[:, 0] == 0).all() and (out[:, -1] == 0).all()
+        out = out[1:-1, 1:-1]
+    xf = x.float().permute(2, 0, 1).unsqueeze(0)
+    ref = F.conv_transpose2d(xf, wt.float(), b, stride=2)[0].permute(1, 2, 0)
+    ref = ref + skip.float() @ w2.float().t()
+    err = (out[..., :Cout].float() - ref).abs()
+    assert (err <= 2e-3 + 1e-3 * ref.abs()).all(), err.max().item()
+
+
+def test_conv1x1_with_second_input():
+    """phases=1: two 1x1 convolutions over two same-resolution inputs summed in the accumulator."""
+    _setup()
+    from tests.gpu_util import conv_gemm
+    g = torch.Generator().manual_seed(12)
+    H, W, Cin, Cout, C2 = 24, 40, 72, 48, 24
+    x = torch.randn(H, W, Cin, generator=g).half().cuda()
+    y = torch.randn(H, W, C2, generator=g).half().cuda()
+    w = (torch.randn(1, Cout, Cin, generator=g) / Cin ** 0.5).half().cuda()
+    w2 = (torch.randn(Cout, C2, generator=g) / C2 ** 0.5).half().cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    _, _, out = conv_gemm(x, w, b, taps=1, in2=y, w2=w2, act=L.ACT_GELU)
+    ref = F.gelu(x.float() @ w[0].float().t() + y.float() @ w2.float().t() + b)
+    err = (out[..., :Cout].float() - ref).abs()
+    assert (err <= 2e-3 + 1e-3 * ref.abs()).all(), err.max().item()
+
+
 @pytest.mark.parametrize("Cout,kind", [(3, L.FINAL_ARGMAX), (1, L.FINAL_THRESH), (1, L.FINAL_NONE),
                                        (3, L.FINAL_EGOLANES)])
 def test_conv_final_modes(Cout, kind):

@@ -168,3 +168,45 @@ def test_linearity_at_full_size():
     z = conv_gemm(torch.zeros(322, 642, 128, device="cuda", dtype=torch.half), w, None, taps=9, in_pad=1,
                   out_pad=1, algo=L.ALGO_LINEAR)[2]
     assert (z.float() == 0).all()
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout,ms,bn", [
+    (20, 40, 64, 256, 1, 256),    # BN=256: each CTA stages 128 of the 256 weight rows
+    (33, 47, 128, 128, 2, 128),   # BN=128, two M sub-tiles per CTA; odd number of M tiles -> dummy peer tile
+    (10, 20, 72, 320, 1, 160),    # K tail, two N tiles of 160
+    (40, 80, 192, 200, 1, 208),   # N tail inside the second CTA's half (BN=208)
+    (16, 16, 64, 128, 1, 128),    # three M tiles only
+    (80, 160, 512, 512, 1, 0),    # decode_layer_4 at full size
+    (160, 320, 256, 128, 2, 0),   # decode_layer_7 at full size
+])
+def test_cta_pair_kernel_matches_torch_and_single_cta_kernel(H, W, Cin, Cout, ms, bn):
+    """conv3x3_pair_kernel (tcgen05.mma.cta_group::2, M = 256 across two CTAs of a cluster, each CTA
+    staging half of every weight tile) against torch fp32 and BIT-EXACT against the 1-CTA kernel: both
+    accumulate the same products in the same K order in fp32."""
+    _setup()
+    from tests.gpu_util import conv_gemm, pad_img
+    x, w, b = _mk(H, W, Cin, Cout, seed=31 + H + Cout)
+    xp = pad_img(x)
+    kw = dict(taps=9, act=L.ACT_GELU, in_pad=1, out_pad=1, algo=L.ALGO_LINEAR, ms=ms, bn=bn)
+    _, _, out = conv_gemm(xp, w, b, pair=1, **kw)
+    _, _, one = conv_gemm(xp, w, b, pair=-1, **kw)
+    assert torch.isfinite(out.float()).all(), "border or interior left unwritten"
+    assert torch.equal(out, one)
+    ref = F.gelu(_ref3(x, w, b, Cin)).permute(1, 2, 0)
+    err = (out[1:-1, 1:-1, :Cout].float() - ref).abs()
+    assert (err <= 1.5e-3 + 1e-3 * ref.abs()).all(), err.max().item()
+
+
+def test_cta_pair_kernel_final_and_residual_modes():
+    _setup()
+    from tests.gpu_util import conv_gemm, pad_img
+    x, w, b = _mk(24, 40, 128, 256, seed=77)
+    bn = 256
+    f = torch.randn(24, 40, 256).half().cuda()
+    kw = dict(taps=9, act=L.ACT_GELU, mode=L.EPI_MULADD, res=f, in_pad=1, out_pad=1, res_pad=0, algo=L.ALGO_LINEAR, bn=bn)
+    _, _, a = conv_gemm(pad_img(x), w, b, pair=1, **kw)
+    _, _, c = conv_gemm(pad_img(x), w, b, pair=-1, **kw)
+    assert torch.equal(a, c)
+    y = F.gelu(_ref3(x, w, b, 128)).permute(1, 2, 0)
+    ref = y * f.float() + f.float()
+    assert ((a[1:-1, 1:-1].float() - ref).abs() <= 3e-3 + 1e-3 * ref.abs()).all()
