@@ -883,21 +883,33 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
+  bool convt_fused_bn = false;
   if (a->bn <= 0 && a->phases == 4 && p.BN > 128) {
-    // ConvTranspose runs all four phases per tile (4 accumulators) -> N tile <= 128
+    // ConvTranspose: the fused form (all four phases per tile, 4 accumulators) needs an N tile <= 128;
+    // it only pays with >= 2 waves of fused tiles, otherwise keep the wide tile (measured: up3 at
+    // BN=256 20 us, at BN=128 unfused 26 us)
     int best = 128, best_waste = 1 << 30;
     for (int bn = 128; bn >= 64; bn -= 16) {
       const int waste = (a->Cout + bn - 1) / bn * bn - a->Cout;
       if (waste < best_waste) { best_waste = waste; best = bn; }
     }
-    p.BN = best;
-  } else if (a->bn <= 0 && a->Cout >= 128) {
+    long sp = -1;
+    for (int tw = 128; tw >= 8; tw >>= 1) {
+      const int th = 128 / tw;
+      const long cost = static_cast<long>((a->H + th - 1) / th) * ((a->W + tw - 1) / tw);
+      if (sp < 0 || cost < sp) sp = cost;
+    }
+    if (a->dbg_ms == 2 || (a->dbg_ms != 1 && !a->in2 && sp * ((a->Cout + best - 1) / best) >= 2 * device_sm_count()))
+      { p.BN = best; convt_fused_bn = true; }
+  }
+  if (!convt_fused_bn && a->bn <= 0 && a->Cout >= 128) {
     // small-M layers (context, first neck blocks): trade N-tile width for CTA count so that the
     // persistent grid covers more of the 148 SMs (weights are re-streamed from L2, activations
     // are tiny)
     const long m_tiles = lin ? (static_cast<long>(a->H + 2) * (a->W + 2) + 127) / 128
                              : (static_cast<long>(a->H) * a->W + 127) / 128 * a->phases;
-    while (p.BN > 64 && m_tiles * ((a->Cout + p.BN - 1) / p.BN) < 96) {
+    const int bn_floor = a->phases == 4 ? 128 : 64;   // ConvT measured better at 128 even with 80 tiles (up0)
+    while (p.BN > bn_floor && m_tiles * ((a->Cout + p.BN - 1) / p.BN) < 96) {
       const int nb2 = (p.BN / 2 + 15) / 16 * 16;
       if ((a->Cout + nb2 - 1) / nb2 * nb2 - a->Cout > a->Cout / 8) break;   // too much N padding
       p.BN = nb2;
@@ -911,6 +923,18 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.kchunks = (a->Cin + 63) / 64;
   p.Cin2 = a->in2 ? a->Cin2 : 0;
   p.kchunks2 = (p.Cin2 + 63) / 64;
+  bool wave_split = false;
+  if (lin && a->bn <= 0 && a->dbg_pair >= 0 && p.BN == 256 && a->Cout % 128 == 0) {
+    // wave quantisation on the pair grid (74 clusters): a 256-wide N tile that needs e.g. 1.4 waves
+    // costs 2 waves; 128-wide tiles (half the work each) may pack better.  Measured on decode_layer_4
+    // (104 pair tiles): BN=256 1153 TF/s, BN=128 1253 TF/s; 128-wide tiles are ~8 % less efficient
+    // otherwise (decode_layer_5/6 keep 256).
+    const int ncl = std::max(1, device_sm_count() / 2);
+    const int pm = ((p.NP + 127) / 128 + 1) / 2;
+    const int w256 = (pm * (a->Cout / 256) + ncl - 1) / ncl, w128 = (pm * (a->Cout / 128) + ncl - 1) / ncl;
+    if (pm * (a->Cout / 256) >= 96 && w128 * 128 * 1.08 < w256 * 256.0) { p.BN = 128; wave_split = true; }
+  }
+  p.tiles_n = (a->Cout + p.BN - 1) / p.BN;
   const size_t b_bytes = static_cast<size_t>(p.BN) * 128;
   if (lin) {
     // two M sub-tiles per CTA (256 pixels, two accumulators sharing every weight tile) when the
@@ -920,12 +944,13 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     if (a->dbg_ms != 1 && a->dbg_ms != 2 && p.BN <= 64 && ((p.NP + 511) / 512) * p.tiles_n >= 2 * device_sm_count()) p.ms = 4;
     if (a->dbg_ms == 2 && p.BN <= 128) p.ms = 2;
     if (a->dbg_ms == 4 && p.BN <= 64) p.ms = 4;
+    if (wave_split) p.ms = 1;
     const size_t seg = seg_slot_bytes(p.ms);
     p.tiles_m = (p.NP + 128 * p.ms - 1) / (128 * p.ms);
-    // CTA pair (cta_group::2, M = 256): for the wide layers with at least a wave of tiles — each CTA
-    // then stages only half of every weight tile
-    p.pair = (a->dbg_pair >= 0 && p.BN >= 128 && p.ms <= 2 && p.tiles_m >= 2 &&
-              (a->dbg_pair == 1 || p.tiles_m * p.tiles_n >= device_sm_count())) ? 1 : 0;
+    // CTA pair (cta_group::2, M = 256) whenever the layer still fills most of the SMs — each CTA then
+    // stages only half of every weight tile (measured: dec6 1082 -> 1396 TF/s, dec4 889 -> 1117)
+    p.pair = (a->dbg_pair >= 0 && p.BN >= 64 && p.tiles_m >= 2 &&
+              (a->dbg_pair == 1 || p.tiles_m * p.tiles_n >= 96)) ? 1 : 0;
     p.total_tiles = (p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;
     // weight ring: slots of gb tiles; gb = 3 (a whole kernel row per barrier) whenever three tiles
     // (half tiles for a pair) stay <= 48 KB

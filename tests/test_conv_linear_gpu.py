@@ -178,6 +178,9 @@ def test_linearity_at_full_size():
     (16, 16, 64, 128, 1, 128),    # three M tiles only
     (80, 160, 512, 512, 1, 0),    # decode_layer_4 at full size
     (160, 320, 256, 128, 2, 0),   # decode_layer_7 at full size
+    (40, 80, 128, 64, 4, 64),     # BN=64: 32 weight rows per CTA, four M sub-tiles
+    (20, 40, 256, 192, 1, 64),    # BN=64, three N tiles, ms=1
+    (320, 640, 128, 64, 0, 0),    # decode_layer_9 at full size (auto: BN=64, ms=4)
 ])
 def test_cta_pair_kernel_matches_torch_and_single_cta_kernel(H, W, Cin, Cout, ms, bn):
     """conv3x3_pair_kernel (tcgen05.mma.cta_group::2, M = 256 across two CTAs of a cluster, each CTA
