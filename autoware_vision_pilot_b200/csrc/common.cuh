@@ -359,6 +359,14 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Division by a launch-time constant d through its reciprocal m = floor(2^32/d) + 1 (m = 0 encodes
+// d = 1): exact whenever x * d < 2^32, which holds for every tile / pixel index here.  One IMAD.HI
+// instead of the ~25-instruction software division on the epilogue's per-tile critical path.
+__host__ __device__ inline uint32_t fast_div_magic(uint32_t d) {
+  return d <= 1 ? 0u : static_cast<uint32_t>((1ull << 32) / d + 1ull);
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t m) { return m ? __umulhi(x, m) : x; }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -70,100 +70,142 @@ struct EpiPix {
   size_t fpix;    // pixel index in the planar fp32 / class outputs (FINAL)
 };
 
-template <class E>
-__device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_row, int n0,
-                                              const float* sbias, int part, const EpiPix& px) {
+// NC = 16-column chunks handled per loop iteration.  The epilogue warps are latency-bound (4 warps per
+// scheduler, one dependent chain each: ncu shows ~16 cycles per issued instruction), so with NC = 2 both
+// TMEM loads are issued before the single wait and every later phase works on two independent chunks
+// the scheduler can interleave.  Measured (gpurun_out/bench_conv_v14_nc{1,2}.txt): NC = 2 is 2-3 % SLOWER —
+// 18 warps leave 96 registers per thread (5 warps on two of the SM sub-partitions) and the second chunk
+// spills; NC = 1 is the default, VPB_EPI_NC=2 selects the other for experiments.
+template <class E, int NC>
+__device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t_row, int n0,
+                                                const float* sbias, int part, const EpiPix& px) {
   const int nchunks = p.BN >> 4;
   typename E::T* out = reinterpret_cast<typename E::T*>(p.out);
   const typename E::T* res = reinterpret_cast<const typename E::T*>(p.res);
-  for (int chunk = part; chunk < nchunks; chunk += 4) {
-    uint32_t rr[16];
-    tmem_ld16(t_row + chunk * 16, rr);
-    tmem_ld_wait();
-    const int n = n0 + chunk * 16;
-    const float4* sb4 = reinterpret_cast<const float4*>(sbias + chunk * 16);   // 4 x LDS.128
-    float v[16];
+  for (int chunk0 = part; chunk0 < nchunks; chunk0 += 4 * NC) {
+    uint32_t rr[NC][16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 b4 = sb4[i];
-      const float2 lo = fadd2(make_float2(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1])), make_float2(b4.x, b4.y));
-      const float2 hi = fadd2(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(b4.z, b4.w));
-      v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
+    for (int c = 0; c < NC; ++c) tmem_ld16(t_row + (chunk0 + 4 * c) * 16, rr[c]);
+    tmem_ld_wait();
+    float v[NC][16];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4* sb4 = reinterpret_cast<const float4*>(sbias + (chunk0 + 4 * c) * 16);   // 4 x LDS.128
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b4 = sb4[i];
+        const float2 lo = fadd2(make_float2(__uint_as_float(rr[c][4 * i]), __uint_as_float(rr[c][4 * i + 1])), make_float2(b4.x, b4.y));
+        const float2 hi = fadd2(make_float2(__uint_as_float(rr[c][4 * i + 2]), __uint_as_float(rr[c][4 * i + 3])), make_float2(b4.z, b4.w));
+        v[c][4 * i] = lo.x; v[c][4 * i + 1] = lo.y; v[c][4 * i + 2] = hi.x; v[c][4 * i + 3] = hi.y;
+      }
     }
     // activation switch hoisted out of the element loop (act(0) == 0 for GELU/SiLU keeps the
     // channel padding zero; sigmoid is masked explicitly)
     if (p.act == ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {   // packed fp32x2: two elements per FFMA2 / FMUL2
-        const float2 g = act_gelu2(make_float2(v[2 * i], v[2 * i + 1]));
-        v[2 * i] = g.x; v[2 * i + 1] = g.y;
-      }
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {   // packed fp32x2: two elements per FFMA2 / FMUL2
+          const float2 g = act_gelu2(make_float2(v[c][2 * i], v[c][2 * i + 1]));
+          v[c][2 * i] = g.x; v[c][2 * i + 1] = g.y;
+        }
     } else if (p.act == ACT_SILU) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = act_silu(v[i]);
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[c][i] = act_silu(v[c][i]);
     } else if (p.act == ACT_SIGMOID) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = (n + i < p.Cout) ? act_sigmoid(v[i]) : 0.f;
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[c][i] = (n0 + (chunk0 + 4 * c) * 16 + i < p.Cout) ? act_sigmoid(v[c][i]) : 0.f;
     }
     if (p.mode == VPB_EPI_FINAL) {
-      if (px.ok && chunk == 0) {
+      if (px.ok && chunk0 == 0) {
         const size_t plane = static_cast<size_t>(p.H) * p.W;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (i < p.Cout) p.out_f32[i * plane + px.fpix] = v[i];
+          if (i < p.Cout) p.out_f32[i * plane + px.fpix] = v[0][i];
         if (p.out_cls) {
           uint8_t cls = 0;
           if (p.final_kind == VPB_FINAL_ARGMAX) {
-            float best = v[0];
+            float best = v[0][0];
 #pragma unroll
             for (int i = 1; i < 16; ++i)
-              if (i < p.Cout && v[i] > best) { best = v[i]; cls = static_cast<uint8_t>(i); }
+              if (i < p.Cout && v[0][i] > best) { best = v[0][i]; cls = static_cast<uint8_t>(i); }
           } else if (p.final_kind == VPB_FINAL_THRESH) {
-            cls = v[0] > 0.f ? 1 : 0;
+            cls = v[0][0] > 0.f ? 1 : 0;
           } else if (p.final_kind == VPB_FINAL_EGOLANES) {
-            cls = (v[2] > 0.f) ? 2 : (v[1] > 0.f) ? 1 : (v[0] > 0.f) ? 0 : 255;
+            cls = (v[0][2] > 0.f) ? 2 : (v[0][1] > 0.f) ? 1 : (v[0][0] > 0.f) ? 0 : 255;
           }
           p.out_cls[px.fpix] = cls;
         }
       }
     } else if (px.ok) {
       if (p.mode == VPB_EPI_ADD || p.mode == VPB_EPI_MULADD) {
-        const typename E::T* rp = res + px.rpix * p.ldr + n;
+        uint4 rv[NC][2];
+        bool rok[NC][2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (n + 8 * j < p.ldr && n + 8 * j < p.ldo) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(rp + 8 * j);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+        for (int c = 0; c < NC; ++c) {          // all residual loads in flight before the first use
+          const int n = n0 + (chunk0 + 4 * c) * 16;
+          const typename E::T* rp = res + px.rpix * p.ldr + n;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            rok[c][j] = (n + 8 * j < p.ldr) && (n + 8 * j < p.ldo);
+            rv[c][j] = rok[c][j] ? *reinterpret_cast<const uint4*>(rp + 8 * j) : make_uint4(0, 0, 0, 0);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (!rok[c][j]) continue;
+            const uint32_t rw[4] = {rv[c][j].x, rv[c][j].y, rv[c][j].z, rv[c][j].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 f = unpack2<E>(rw[i]);
-              float& a = v[8 * j + 2 * i];
-              float& b = v[8 * j + 2 * i + 1];
+              float& a = v[c][8 * j + 2 * i];
+              float& b = v[c][8 * j + 2 * i + 1];
               if (p.mode == VPB_EPI_ADD) { a += f.x; b += f.y; }
               else { a = fmaf(a, f.x, f.x); b = fmaf(b, f.y, f.y); }
             }
           }
-        }
       }
-      typename E::T* op = out + px.opix * p.ldo + n;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (n + 8 * j < p.ldo) {
-          uint4 o;
-          o.x = pack2<E>(v[8 * j + 0], v[8 * j + 1]);
-          o.y = pack2<E>(v[8 * j + 2], v[8 * j + 3]);
-          o.z = pack2<E>(v[8 * j + 4], v[8 * j + 5]);
-          o.w = pack2<E>(v[8 * j + 6], v[8 * j + 7]);
-          *reinterpret_cast<uint4*>(op + 8 * j) = o;
+      for (int c = 0; c < NC; ++c) {
+        const int n = n0 + (chunk0 + 4 * c) * 16;
+        typename E::T* op = out + px.opix * p.ldo + n;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (n + 8 * j < p.ldo) {
+            uint4 o;
+            o.x = pack2<E>(v[c][8 * j + 0], v[c][8 * j + 1]);
+            o.y = pack2<E>(v[c][8 * j + 2], v[c][8 * j + 3]);
+            o.z = pack2<E>(v[c][8 * j + 4], v[c][8 * j + 5]);
+            o.w = pack2<E>(v[c][8 * j + 6], v[c][8 * j + 7]);
+            *reinterpret_cast<uint4*>(op + 8 * j) = o;
+          }
         }
       }
     } else if (px.zero) {
-      typename E::T* op = out + px.opix * p.ldo + n;
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (n + 8 * j < p.ldo) *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < NC; ++c) {
+        const int n = n0 + (chunk0 + 4 * c) * 16;
+        typename E::T* op = out + px.opix * p.ldo + n;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (n + 8 * j < p.ldo) *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(0, 0, 0, 0);
+      }
     }
   }
+}
+
+template <class E>
+__device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_row, int n0,
+                                              const float* sbias, int part, const EpiPix& px) {
+  // every warp owns chunks part, part+4, ...: pairs exist when the chunk count is a multiple of 8
+  if (p.nc2 && ((p.BN >> 4) & 7) == 0) epilogue_chunks<E, 2>(p, t_row, n0, sbias, part, px);
+  else epilogue_chunks<E, 1>(p, t_row, n0, sbias, part, px);
 }
 
 __device__ __forceinline__ void stage_bias(const ConvKParams& p, float* dst, int etid, int n0) {
@@ -240,12 +282,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int ph = tile / tiles_per_phase;
+      const int ph = static_cast<int>(fast_div(tile, p.mg_tpp));
       int r = tile - ph * tiles_per_phase;
-      const int nt = r % p.tiles_n;
-      r /= p.tiles_n;
-      const int twi = r % p.tiles_w;
-      const int thi = r / p.tiles_w;
+      const int rn = static_cast<int>(fast_div(r, p.mg_tn));
+      const int nt = r - rn * p.tiles_n;
+      const int thi = static_cast<int>(fast_div(rn, p.mg_tw));
+      const int twi = rn - thi * p.tiles_w;
       const int h0 = thi * p.TH, w0 = twi * p.TW, n0 = nt * p.BN;
       for (int t = 0; t < p.taps; ++t) {
         const int dy = (p.taps == 9) ? (t / 3 - 1) : 0;
@@ -341,12 +383,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = p.fuse4 ? 0 : (it & 1);
       const uint32_t aphase = p.fuse4 ? (it & 1) : ((it >> 1) & 1);
-      const int ph0 = p.fuse4 ? 0 : tile / tiles_per_phase;
-      int r = tile - ph0 * tiles_per_phase;
-      const int nt = r % p.tiles_n;
-      r /= p.tiles_n;
-      const int twi = r % p.tiles_w;
-      const int thi = r / p.tiles_w;
+      const int ph0 = p.fuse4 ? 0 : static_cast<int>(fast_div(tile, p.mg_tpp));
+      const int r = tile - ph0 * tiles_per_phase;
+      const int rn = static_cast<int>(fast_div(r, p.mg_tn));
+      const int nt = r - rn * p.tiles_n;
+      const int thi = static_cast<int>(fast_div(rn, p.mg_tw));
+      const int twi = rn - thi * p.tiles_w;
       const int h = thi * p.TH + lh, w = twi * p.TW + lw, n0 = nt * p.BN;
 
       stage_bias(p, s_bias[as], etid, n0);
@@ -431,7 +473,7 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+      const int mt = static_cast<int>(fast_div(tile, p.mg_tn)), nt = tile - mt * p.tiles_n;
       const int p0 = mt * tile_px, n0 = nt * p.BN;
       for (int c = 0; c < p.kchunks; ++c) {
         for (int dy = 0; dy < 3; ++dy) {
@@ -567,14 +609,14 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+      const int mt = static_cast<int>(fast_div(tile, p.mg_tn)), nt = tile - mt * p.tiles_n;
       const int n0 = nt * p.BN;
       stage_bias(p, s_bias[as], etid, n0);
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
       for (int half = 0; half < p.ms; ++half) {
         const int pp = mt * tile_px + half * 128 + row;          // linear padded pixel index
-        const int y = pp / p.WP, x = pp - y * p.WP;
+        const int y = static_cast<int>(fast_div(pp, p.mg_wp)), x = pp - y * p.WP;
         const bool inside = (pp < p.NP) && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
         EpiPix px;
         px.ok = inside;
@@ -667,7 +709,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA,
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     for (int tile = cid; tile < p.total_tiles; tile += ncl) {
-      const int nt = tile % p.tiles_n, pm = tile / p.tiles_n;
+      const int pm = static_cast<int>(fast_div(tile, p.mg_tn)), nt = tile - pm * p.tiles_n;
       const int p0 = (pm * 2 + static_cast<int>(rank)) * tile_px;
       const int n0 = nt * p.BN + static_cast<int>(rank) * (p.BN >> 1);
       for (int c = 0; c < p.kchunks; ++c) {
@@ -757,7 +799,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA,
     for (int tile = cid; tile < p.total_tiles; tile += ncl, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int nt = tile % p.tiles_n, pm = tile / p.tiles_n;
+      const int pm = static_cast<int>(fast_div(tile, p.mg_tn)), nt = tile - pm * p.tiles_n;
       const int mt = pm * 2 + static_cast<int>(rank);
       const int n0 = nt * p.BN;
       stage_bias(p, s_bias[as], etid, n0);
@@ -765,7 +807,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA,
       tc_fence_after();
       for (int half = 0; half < p.ms; ++half) {
         const int pp = mt * tile_px + half * 128 + row;
-        const int y = pp / p.WP, x = pp - y * p.WP;
+        const int y = static_cast<int>(fast_div(pp, p.mg_wp)), x = pp - y * p.WP;
         const bool inside = (pp < p.NP) && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
         EpiPix px;
         px.ok = inside;
@@ -881,6 +923,11 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.in_pad = a->in_pad ? 1 : 0; p.out_pad = a->out_pad ? 1 : 0; p.res_pad = a->res_pad ? 1 : 0;
   p.lin = lin ? 1 : 0;
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
+  {
+    static int nc = -1;   // experiment hook: VPB_EPI_NC=2 enables the two-chunks-per-iteration epilogue
+    if (nc < 0) { const char* e = getenv("VPB_EPI_NC"); nc = (e && e[0] == '2') ? 2 : 1; }
+    p.nc2 = nc == 2 ? 1 : 0;
+  }
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
   bool convt_fused_bn = false;
@@ -987,6 +1034,8 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     p.stages = std::max(2, std::min(stages, kMaxStages));
     plan->smem_bytes = p.stages * stage_bytes + 1024;
   }
+  p.mg_tn = fast_div_magic(p.tiles_n); p.mg_tw = fast_div_magic(lin ? 1 : p.tiles_w);
+  p.mg_tpp = fast_div_magic(lin ? 1 : p.tiles_n * p.tiles_h * p.tiles_w); p.mg_wp = fast_div_magic(p.WP);
   p.act = a->act; p.mode = a->mode; p.final_kind = a->final_kind;
   p.bias = a->bias; p.out = a->out; p.ldo = a->ldo; p.res = a->res; p.ldr = a->ldr;
   p.out_f32 = a->out_f32; p.out_cls = a->out_cls;
