@@ -93,6 +93,7 @@ struct OpRec {
   std::function<int(cudaStream_t)> launch;
   double flops = 0;
   bool gemm = false;
+  int kind = 0;   // 0 = not a convolution GEMM, 1 = conv_gemm_kernel, 2 = conv3x3_lin_kernel, 3 = conv3x3_pair_kernel
   int lane = 0;   // execution lane (= index of the model that owns the op); lanes run concurrently
 };
 
@@ -231,6 +232,7 @@ struct vp_engine {
     ConvPlan* pp = plan.get();
     plans.push_back(std::move(plan));
     OpRec op; op.name = name; op.flops = pp->flops; op.gemm = true; op.lane = cur_lane;
+    op.kind = pp->p.lin ? (pp->p.pair ? 3 : 2) : 1;
     op.launch = [pp](cudaStream_t s) { return conv_plan_launch(pp, s); };
     ops.push_back(std::move(op));
     return VPB_OK;
@@ -861,7 +863,7 @@ extern "C" int vp_engine_profile(vp_engine* e, int max_ops, float* ms, double* f
     VPB_CUDA_OK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
     if (flops) flops[i] = i == 0 ? 0.0 : e->ops[i - 1].flops;
     if (names) names[i] = i == 0 ? kPre : e->ops[i - 1].name.c_str();
-    if (is_gemm) is_gemm[i] = i == 0 ? 0 : (e->ops[i - 1].gemm ? 1 : 0);
+    if (is_gemm) is_gemm[i] = i == 0 ? 0 : (e->ops[i - 1].gemm ? e->ops[i - 1].kind : 0);
   }
   for (auto& x : ev) cudaEventDestroy(x);
   return VPB_OK;

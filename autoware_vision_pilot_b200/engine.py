@@ -160,8 +160,9 @@ class Engine:
         cnt = C.c_int()
         gemm = (C.c_int * n)()
         L.check(self._lib.vp_engine_profile(self._h, n, ms, fl, names, gemm, C.byref(cnt)), "vp_engine_profile")
-        return [{"name": names[i].decode(), "ms": ms[i], "flops": fl[i], "gemm": bool(gemm[i])}
-                for i in range(cnt.value)]
+        kern = {1: "conv_gemm_kernel", 2: "conv3x3_lin_kernel", 3: "conv3x3_pair_kernel"}
+        return [{"name": names[i].decode(), "ms": ms[i], "flops": fl[i], "gemm": bool(gemm[i]),
+                 "kernel": kern.get(gemm[i])} for i in range(cnt.value)]
 
     def read_resized(self) -> np.ndarray:
         buf = np.empty((320, 640, 3), dtype=np.uint8)

@@ -109,7 +109,8 @@ typedef struct {
 } vp_engine_stats;
 int vp_engine_get_stats(const vp_engine* e, vp_engine_stats* s);
 /* Eagerly run one frame with a CUDA-event pair around every kernel; returns the per-kernel
- * device times (ms) in launch order; is_gemm[i] = 1 for the tcgen05 convolution launches.
+ * device times (ms) in launch order; is_gemm[i] != 0 for the tcgen05 convolution launches
+ * (1 = conv_gemm_kernel, 2 = conv3x3_lin_kernel, 3 = conv3x3_pair_kernel), 0 otherwise.
  * names[i] point into engine-owned storage. */
 int vp_engine_profile(vp_engine* e, int max_ops, float* ms, double* flops, const char** names,
                       int* is_gemm, int* n_ops);
