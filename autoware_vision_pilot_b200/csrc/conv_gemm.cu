@@ -65,9 +65,9 @@ static constexpr int kMaxRing = 16;
 struct EpiPix {
   bool ok;        // compute and store this row
   bool zero;      // store zeros instead (border pixel of a padded output)
-  size_t opix;    // pixel index in the output tensor
-  size_t rpix;    // pixel index in the residual tensor
-  size_t fpix;    // pixel index in the planar fp32 / class outputs (FINAL)
+  uint32_t ooff;  // element offset of the pixel in the output tensor   (pixel * ldo; < 2^31, checked by the plan)
+  uint32_t roff;  // element offset of the pixel in the residual tensor (pixel * ldr)
+  uint32_t fpix;  // pixel index in the planar fp32 / class outputs (FINAL)
 };
 
 // NC = 16-column chunks handled per loop iteration.  The epilogue warps are latency-bound (4 warps per
@@ -75,7 +75,7 @@ struct EpiPix {
 // TMEM loads are issued before the single wait and every later phase works on two independent chunks
 // the scheduler can interleave.  Measured (gpurun_out/bench_conv_v14_nc{1,2}.txt): NC = 2 is 2-3 % SLOWER —
 // 18 warps leave 96 registers per thread (5 warps on two of the SM sub-partitions) and the second chunk
-// spills; NC = 1 is the default, VPB_EPI_NC=2 selects the other for experiments.
+// spills; only NC = 1 is instantiated.
 template <class E, int NC>
 __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t_row, int n0,
                                                 const float* sbias, int part, const EpiPix& px) {
@@ -122,7 +122,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
     }
     if (p.mode == VPB_EPI_FINAL) {
       if (px.ok && chunk0 == 0) {
-        const size_t plane = static_cast<size_t>(p.H) * p.W;
+        const uint32_t plane = static_cast<uint32_t>(p.H * p.W);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (i < p.Cout) p.out_f32[i * plane + px.fpix] = v[0][i];
@@ -148,7 +148,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
 #pragma unroll
         for (int c = 0; c < NC; ++c) {          // all residual loads in flight before the first use
           const int n = n0 + (chunk0 + 4 * c) * 16;
-          const typename E::T* rp = res + px.rpix * p.ldr + n;
+          const typename E::T* rp = res + (px.roff + n);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             rok[c][j] = (n + 8 * j < p.ldr) && (n + 8 * j < p.ldo);
@@ -174,7 +174,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int n = n0 + (chunk0 + 4 * c) * 16;
-        typename E::T* op = out + px.opix * p.ldo + n;
+        typename E::T* op = out + (px.ooff + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if (n + 8 * j < p.ldo) {
@@ -191,7 +191,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int n = n0 + (chunk0 + 4 * c) * 16;
-        typename E::T* op = out + px.opix * p.ldo + n;
+        typename E::T* op = out + (px.ooff + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
           if (n + 8 * j < p.ldo) *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(0, 0, 0, 0);
@@ -203,9 +203,9 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
 template <class E>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_row, int n0,
                                               const float* sbias, int part, const EpiPix& px) {
-  // every warp owns chunks part, part+4, ...: pairs exist when the chunk count is a multiple of 8
-  if (p.nc2 && ((p.BN >> 4) & 7) == 0) epilogue_chunks<E, 2>(p, t_row, n0, sbias, part, px);
-  else epilogue_chunks<E, 1>(p, t_row, n0, sbias, part, px);
+  // NC = 2 (two chunks per iteration) measured 2-3 % slower and makes ptxas spill in every kernel that
+  // contains it (96-register cap), so only the one-chunk form is instantiated.
+  epilogue_chunks<E, 1>(p, t_row, n0, sbias, part, px);
 }
 
 __device__ __forceinline__ void stage_bias(const ConvKParams& p, float* dst, int etid, int n0) {
@@ -401,9 +401,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
         EpiPix px;
         px.ok = (h < p.H) && (w < p.W);
         px.zero = false;
-        px.opix = static_cast<size_t>(oh + p.out_pad) * (Wo + 2 * p.out_pad) + (ow + p.out_pad);
-        px.rpix = static_cast<size_t>(oh + p.res_pad) * (Wo + 2 * p.res_pad) + (ow + p.res_pad);
-        px.fpix = static_cast<size_t>(h) * p.W + w;
+        px.ooff = static_cast<uint32_t>((oh + p.out_pad) * (Wo + 2 * p.out_pad) + (ow + p.out_pad)) * p.ldo;
+        px.roff = static_cast<uint32_t>((oh + p.res_pad) * (Wo + 2 * p.res_pad) + (ow + p.res_pad)) * p.ldr;
+        px.fpix = static_cast<uint32_t>(h * p.W + w);
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + q4 * 128;
         epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
       }
@@ -615,18 +615,23 @@ conv3x3_lin_kernel(const __grid_constant__ CUtensorMap mapA,
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
       for (int half = 0; half < p.ms; ++half) {
+        // a 16-wide N tile (the heads' last conv) has one column chunk: instead of leaving three of the
+        // four warps of a quadrant idle, the M sub-tiles are dealt out to them (ncu: dec10 was bound by
+        // 4 of 16 epilogue warps walking all sub-tiles serially)
+        int epart = part;
+        if (p.BN == 16) { if (part != (half & 3)) continue; epart = 0; }
         const int pp = mt * tile_px + half * 128 + row;          // linear padded pixel index
         const int y = static_cast<int>(fast_div(pp, p.mg_wp)), x = pp - y * p.WP;
         const bool inside = (pp < p.NP) && y >= 1 && y <= p.H && x >= 1 && x <= p.W;
         EpiPix px;
         px.ok = inside;
         px.zero = (pp < p.NP) && !inside && p.out_pad;
-        const size_t upix = static_cast<size_t>(y - 1) * p.W + (x - 1);   // unpadded index (if inside)
-        px.opix = p.out_pad ? static_cast<size_t>(pp) : upix;
-        px.rpix = p.res_pad ? static_cast<size_t>(pp) : upix;
+        const uint32_t upix = static_cast<uint32_t>((y - 1) * p.W + (x - 1));   // unpadded index (if inside)
+        px.ooff = (p.out_pad ? static_cast<uint32_t>(pp) : upix) * p.ldo;
+        px.roff = (p.res_pad ? static_cast<uint32_t>(pp) : upix) * p.ldr;
         px.fpix = upix;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * acc_cols;
-        epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
+        epilogue_tile<E>(p, t_row, n0, s_bias[as], epart, px);
       }
       tc_fence_before();
       __syncwarp();
@@ -812,9 +817,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA,
         EpiPix px;
         px.ok = inside;
         px.zero = (pp < p.NP) && !inside && p.out_pad;
-        const size_t upix = static_cast<size_t>(y - 1) * p.W + (x - 1);
-        px.opix = p.out_pad ? static_cast<size_t>(pp) : upix;
-        px.rpix = p.res_pad ? static_cast<size_t>(pp) : upix;
+        const uint32_t upix = static_cast<uint32_t>((y - 1) * p.W + (x - 1));   // unpadded index (if inside)
+        px.ooff = (p.out_pad ? static_cast<uint32_t>(pp) : upix) * p.ldo;
+        px.roff = (p.res_pad ? static_cast<uint32_t>(pp) : upix) * p.ldr;
         px.fpix = upix;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + half * acc_cols;
         epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
@@ -911,6 +916,14 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
       return VPB_ERR_ARG;
     }
   }
+  {
+    // the epilogue addresses pixels with 32-bit element offsets
+    const long ho = a->phases == 4 ? 2L * a->H + 2 : a->H + 2, wo = a->phases == 4 ? 2L * a->W + 2 : a->W + 2;
+    if (ho * wo * std::max(a->ldo, a->ldr) >= (1L << 31) || static_cast<long>(a->H) * a->W * 16 >= (1L << 31)) {
+      vpb_set_error("conv: tensor too large for 32-bit element offsets");
+      return VPB_ERR_ARG;
+    }
+  }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     vpb_set_error("conv: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -923,11 +936,6 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.in_pad = a->in_pad ? 1 : 0; p.out_pad = a->out_pad ? 1 : 0; p.res_pad = a->res_pad ? 1 : 0;
   p.lin = lin ? 1 : 0;
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
-  {
-    static int nc = -1;   // experiment hook: VPB_EPI_NC=2 enables the two-chunks-per-iteration epilogue
-    if (nc < 0) { const char* e = getenv("VPB_EPI_NC"); nc = (e && e[0] == '2') ? 2 : 1; }
-    p.nc2 = nc == 2 ? 1 : 0;
-  }
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
   bool convt_fused_bn = false;
@@ -1004,8 +1012,12 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     p.gb = (p.pair || (a->dbg_gb != 1 && p.BN <= 144)) ? 3 : 1;
     const size_t slot = (p.pair ? b_bytes / 2 : b_bytes) * p.gb;
     const size_t budget = kMaxDynSmem - 1024;
-    p.na = p.ms >= 2 ? 3 : (p.BN >= 256 ? 3 : 4);
-    while (p.na > 2 && static_cast<size_t>(p.na) * seg + 3 * slot > budget) --p.na;
+    // One ring round trip costs ~3.1 k cycles whatever the box size (profiles/r1_tma_ring_microbench.md), so
+    // what matters is how many (activation segment + kernel-row weight slot) GROUPS are in flight: balance
+    // the two rings (the K-heavy small layers were running with 4 segments against 6+ weight slots)
+    const int groups = static_cast<int>(budget / (seg + (p.gb == 3 ? slot : 3 * slot)));
+    p.na = std::max(2, std::min(kMaxRing, groups));
+    while (p.na > 2 && static_cast<size_t>(p.na) * seg + 2 * slot > budget) --p.na;
     p.nb = static_cast<int>(std::min<size_t>(kMaxRing, (budget - static_cast<size_t>(p.na) * seg) / slot));
     if (p.nb < 2) { vpb_set_error("conv: no room for the weight ring"); return VPB_ERR_ARG; }
     plan->smem_bytes = static_cast<size_t>(p.na) * seg + p.nb * slot + 1024;

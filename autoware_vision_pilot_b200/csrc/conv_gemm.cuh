@@ -27,7 +27,6 @@ struct ConvKParams {
   int NP, WP, tiles_m;           // linear kernel: padded pixel count, padded width, M tiles
   int in_pad, out_pad, res_pad;  // 1 = that tensor is a zero-bordered image [(H+2)*(W+2)][C]
   uint32_t mg_tn, mg_tw, mg_tpp, mg_wp;  // magic reciprocals (fast_div) of tiles_n, tiles_w, tiles per phase, WP
-  int nc2;                       // epilogue handles two 16-column chunks per iteration (ILP) when possible
   int desc_bo;                   // 1 = set the smem-descriptor base_offset for shifted tap views
   int act, mode, final_kind;
   const float* bias;
