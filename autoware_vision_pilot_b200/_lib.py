@@ -39,6 +39,30 @@ class ConvArgs(C.Structure):
     ]
 
 
+class LateralState(C.Structure):
+    """Mirror of vpb_lateral_state (device-resident, persistent)."""
+
+    _fields_ = [("prev_left", C.c_double * 6), ("prev_right", C.c_double * 6),
+                ("prev_left_valid", C.c_int), ("prev_right_valid", C.c_int),
+                ("last_valid_bev_width", C.c_double), ("has_valid_width_history", C.c_int),
+                ("reserved_", C.c_int)]
+
+
+class LateralOut(C.Structure):
+    """Mirror of vpb_lateral_out."""
+
+    _fields_ = [("left_coeffs", C.c_double * 6), ("right_coeffs", C.c_double * 6), ("center_coeffs", C.c_double * 6),
+                ("bev_left_coeffs", C.c_double * 6), ("bev_right_coeffs", C.c_double * 6),
+                ("bev_center_coeffs", C.c_double * 6),
+                ("lane_offset", C.c_double), ("yaw_offset", C.c_double), ("curvature", C.c_double),
+                ("bev_lane_offset", C.c_double), ("bev_yaw_offset", C.c_double), ("bev_curvature", C.c_double),
+                ("last_valid_width_pixels", C.c_double),
+                ("left_valid", C.c_int), ("right_valid", C.c_int), ("path_valid", C.c_int), ("bev_valid", C.c_int),
+                ("filt_left_valid", C.c_int), ("filt_right_valid", C.c_int),
+                ("left_start", C.c_int * 2), ("right_start", C.c_int * 2),
+                ("n_left_pts", C.c_int), ("n_right_pts", C.c_int)]
+
+
 _lib = None
 
 

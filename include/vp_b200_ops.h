@@ -176,6 +176,43 @@ int vpb_polyfit(const float* xs, const float* ys, const int* offsets, int n_sets
  * state and each measurement are [14][2] doubles (mean, variance); NaN mean = "no measurement". */
 int vpb_bayes_fuse(double* state, const double* meas, int n_meas, void* stream);
 
+/* ---- lateral post-process after EgoLanes, on the device ----
+ * LaneFilter::update (production_release/src/lane_filtering/lane_filter.cpp:232-323: ROI start points
+ * :325-370, sliding-window search :376-590, poly-fit :116-218 = least squares of ALL points, order 1 below
+ * 30 points else 2 — its RANSAC loop can never replace the all-points inlier set —, temporal smoothing)
+ * followed by LaneTracker::update (src/lane_tracking/lane_tracking.cpp:36-300: BEV warp of the fitted
+ * lines sampled every 5 px, lane-width history / recovery of a missing line, curve parameters in both
+ * views).  Coefficient vectors are the reference's 6-vectors [c3, c2, c1, c0, min_y, max_y].
+ * Both structs live in DEVICE memory; the state persists from frame to frame. */
+typedef struct {
+  double prev_left[6], prev_right[6];      /* LaneFilter::prev_*_fit (lane_filter.hpp:100-101)        */
+  int prev_left_valid, prev_right_valid;
+  double last_valid_bev_width;             /* LaneTracker (lane_tracking.hpp:86-87), 180.0 initially  */
+  int has_valid_width_history;
+  int reserved_;
+} vpb_lateral_state;
+typedef struct {
+  double left_coeffs[6], right_coeffs[6], center_coeffs[6];            /* LaneSegmentation (model space) */
+  double bev_left_coeffs[6], bev_right_coeffs[6], bev_center_coeffs[6];/* BEVVisuals                     */
+  double lane_offset, yaw_offset, curvature;                           /* DualViewMetrics orig_*         */
+  double bev_lane_offset, bev_yaw_offset, bev_curvature;               /* DualViewMetrics bev_*          */
+  double last_valid_width_pixels;
+  int left_valid, right_valid;             /* coefficient vector present after tracking (fit or recovered) */
+  int path_valid, bev_valid;
+  int filt_left_valid, filt_right_valid;   /* LaneFilter produced a fit this frame                         */
+  int left_start[2], right_start[2];       /* (x, y) of the ROI start points, -1 if none                   */
+  int n_left_pts, n_right_pts;             /* points collected by the sliding windows                       */
+} vpb_lateral_out;
+/* LaneFilter::reset + LaneTracker defaults */
+int vpb_lateral_init(vpb_lateral_state* state_dev, void* stream);
+/* masks: device float [3][H][W] (ego_left, ego_right, other_lanes; the output of vpb_lane_masks),
+ * H <= 128 (>= 41), W <= 256; img_w x img_h = size of the source frame the homography refers to;
+ * homography: host pointer to 9 doubles (orig -> BEV) or NULL for the reference's matrix
+ * (lane_tracking.hpp:75-79). */
+int vpb_lateral_update(const float* masks, int H, int W, int img_w, int img_h, float smoothing,
+                       const double* homography, vpb_lateral_state* state_dev, vpb_lateral_out* out_dev,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
