@@ -45,7 +45,7 @@ class LateralState(C.Structure):
     _fields_ = [("prev_left", C.c_double * 6), ("prev_right", C.c_double * 6),
                 ("prev_left_valid", C.c_int), ("prev_right_valid", C.c_int),
                 ("last_valid_bev_width", C.c_double), ("has_valid_width_history", C.c_int),
-                ("reserved_", C.c_int)]
+                ("reserved_", C.c_int), ("pf_state", (C.c_double * 2) * 14)]
 
 
 class LateralOut(C.Structure):
@@ -60,7 +60,14 @@ class LateralOut(C.Structure):
                 ("left_valid", C.c_int), ("right_valid", C.c_int), ("path_valid", C.c_int), ("bev_valid", C.c_int),
                 ("filt_left_valid", C.c_int), ("filt_right_valid", C.c_int),
                 ("left_start", C.c_int * 2), ("right_start", C.c_int * 2),
-                ("n_left_pts", C.c_int), ("n_right_pts", C.c_int)]
+                ("n_left_pts", C.c_int), ("n_right_pts", C.c_int),
+                ("pf_left_coeff", C.c_double * 3), ("pf_right_coeff", C.c_double * 3),
+                ("pf_left_cte", C.c_double), ("pf_left_yaw_error", C.c_double),
+                ("pf_right_cte", C.c_double), ("pf_right_yaw_error", C.c_double),
+                ("pf_cte", C.c_double), ("pf_yaw_error", C.c_double), ("pf_curvature", C.c_double),
+                ("pf_lane_width", C.c_double), ("pf_cte_variance", C.c_double), ("pf_yaw_variance", C.c_double),
+                ("pf_curv_variance", C.c_double), ("pf_lane_width_variance", C.c_double),
+                ("pf_fused_valid", C.c_int), ("pf_ran", C.c_int)]
 
 
 _lib = None

@@ -1,8 +1,8 @@
 // lateral.cu — the production lateral post-process that follows EgoLanes, on the device
 // (SURVEY.md §8f rank 1): LaneFilter (ROI start points -> sliding-window search -> poly-fit ->
 // temporal smoothing) and LaneTracker (BEV homography warp of the fitted lines, lane-width recovery
-// of a missing line, curve parameters in both views).  The masks never leave the GPU; what goes to the
-// host is one vpb_lateral_out record.
+// of a missing line, curve parameters in both views) and PathFinder (metric quadratic fits + the 14-slot
+// Bayes filter).  The masks never leave the GPU; what goes to the host is one vpb_lateral_out record.
 //
 // Reference (restated, not copied):
 //   VisionPilot/production_release/src/lane_filtering/lane_filter.cpp  :232-323 update, :325-370
@@ -10,6 +10,8 @@
 //     replace the all-points inlier set — `best_inliers` starts as all points and only a strictly larger
 //     set replaces it — so fitPoly IS the least-squares fit of all points; no sampler here)
 //   VisionPilot/production_release/src/lane_tracking/lane_tracking.cpp :36-300 update, :305-452 helpers
+//   VisionPilot/production_release/src/path_planning/path_finder.cpp :48-181, poly_fit.cpp :26-75,
+//     estimator.cpp :15-74, main.cpp :333-357 (BEV pixels -> metres)
 //
 // One CTA.  All 256 threads turn the three float masks into bit rows in shared memory; warp 0 then
 // runs the (inherently sequential) search with the window scan, the moment sums and the point warps
@@ -225,6 +227,7 @@ struct LatParams {
   double sx, sy;            // image / model scale
   float smoothing;
   double Hm[9], Hi[9];      // orig -> BEV homography and its inverse
+  double steering;          // AutoSteer steering angle handed to PathFinder (main.cpp:577)
 };
 
 // cv::perspectiveTransform for float points with a double matrix
@@ -407,6 +410,71 @@ __global__ void __launch_bounds__(256) lateral_kernel(const float* __restrict__ 
     o.last_valid_width_pixels = width;
     o.bev_valid = 1;
   }
+  // ---- PathFinder::update (path_finder.cpp:48-181) on the BEV points, only when they are valid (main.cpp:565)
+  if (o.bev_valid) {
+    double pf[14][2];
+    for (int i = 0; i < 14; ++i) { pf[i][0] = st->pf_state[i][0]; pf[i][1] = st->pf_state[i][1] + 0.5 * 0.5; }   // predict
+    double coeff[2][3], cte[2], yaw[2];
+    for (int side = 0; side < 2; ++side) {
+      const float* bxp = side == 0 ? s.ax : s.bx;
+      const float* byp = side == 0 ? s.ay : s.by;
+      const int n = side == 0 ? nl : nr;
+      __syncwarp();
+      for (int k = lane; k < n; k += 32) {             // transformPixelsToMeters (main.cpp:333-357)
+        s.cx[k] = static_cast<float>((static_cast<double>(bxp[k]) - 320.0) * (40.0 / 640.0));
+        s.cy[k] = static_cast<float>((640.0 - static_cast<double>(byp[k])) * (40.0 / 640.0));
+      }
+      __syncwarp();
+      if (n > 2) {                                     // fitQuadPoly (poly_fit.cpp:36-75)
+        double c[3], y0, y1;
+        warp_fit(s.cx, s.cy, n, 2, false, c, &y0, &y1);
+        coeff[side][0] = c[2]; coeff[side][1] = c[1]; coeff[side][2] = c[0];
+        cte[side] = -coeff[side][2];                   // FittedCurve (poly_fit.cpp:26-34)
+        yaw[side] = -atan2(coeff[side][1], 1.0);
+      } else {
+        coeff[side][0] = coeff[side][1] = coeff[side][2] = nan("");
+        cte[side] = yaw[side] = nan("");
+      }
+    }
+    const double nanv = nan("");
+    const double w12 = pf[12][0];
+    double mm[14], mv[14];
+    for (int i = 0; i < 4; ++i) { mv[i] = 0.1 * 0.1; mv[4 + i] = 0.01 * 0.01; mv[8 + i] = 0.1 * 0.1; }
+    mv[12] = mv[13] = 0.01 * 0.01;
+    for (int i = 0; i < 14; ++i) mm[i] = nanv;
+    mm[1] = cte[0] + w12 / 2.0; mm[5] = yaw[0]; mm[9] = p.steering;
+    mm[2] = cte[1] - w12 / 2.0; mm[6] = yaw[1]; mm[10] = p.steering;
+    if (isnan(cte[0]) && isnan(cte[1])) mm[12] = 4.0;
+    else if (isnan(cte[0]) || isnan(cte[1])) mm[12] = w12;
+    else mm[12] = cte[1] - cte[0];
+    for (int i = 0; i < 14; ++i) {                     // Estimator::update (estimator.cpp:24-74)
+      const double v0 = pf[i][1], m0 = pf[i][0];
+      if (isnan(mm[i])) { pf[i][1] = v0 * 1.25; continue; }
+      const double v1 = mv[i], m1 = mm[i];
+      pf[i][1] = (v0 * v1) / (v0 + v1);
+      pf[i][0] = (m0 * v1 + m1 * v0) / (v0 + v1);
+    }
+    const int rules[3][2] = {{0, 3}, {5, 7}, {9, 11}};
+    for (int r = 0; r < 3; ++r) {
+      double inv = 0.0, wm = 0.0;
+      for (int i = rules[r][0]; i < rules[r][1]; ++i) {
+        if (pf[i][1] <= 0.0) continue;
+        inv += 1.0 / pf[i][1];
+        wm += pf[i][0] / pf[i][1];
+      }
+      if (inv > 0.0) { const double fv = 1.0 / inv; pf[rules[r][1]][0] = fv * wm; pf[rules[r][1]][1] = fv; }
+    }
+    for (int k = 0; k < 3; ++k) { o.pf_left_coeff[k] = coeff[0][k]; o.pf_right_coeff[k] = coeff[1][k]; }
+    o.pf_left_cte = cte[0]; o.pf_left_yaw_error = yaw[0]; o.pf_right_cte = cte[1]; o.pf_right_yaw_error = yaw[1];
+    o.pf_cte = pf[3][0]; o.pf_yaw_error = pf[7][0]; o.pf_curvature = p.steering; o.pf_lane_width = pf[12][0];
+    o.pf_cte_variance = pf[3][1]; o.pf_yaw_variance = pf[7][1]; o.pf_curv_variance = pf[11][1];
+    o.pf_lane_width_variance = pf[12][1];
+    o.pf_fused_valid = !(isnan(o.pf_cte) || isnan(o.pf_yaw_error) || isnan(o.pf_curvature));
+    o.pf_ran = 1;
+    __syncwarp();
+    if (lane == 0)
+      for (int i = 0; i < 14; ++i) { st->pf_state[i][0] = pf[i][0]; st->pf_state[i][1] = pf[i][1]; }
+  }
   if (lane == 0) {
     st->last_valid_bev_width = width;
     st->has_valid_width_history = has_width;
@@ -426,6 +494,8 @@ __global__ void lateral_init_kernel(vpb_lateral_state* st) {
     st->last_valid_bev_width = 180.0;      // lane_tracking.hpp:86
     st->has_valid_width_history = 0;
     st->reserved_ = 0;
+    for (int i = 0; i < 14; ++i) { st->pf_state[i][0] = 0.0; st->pf_state[i][1] = 1e3; }   // path_finder.cpp:34-43
+    st->pf_state[12][0] = 4.0; st->pf_state[12][1] = 0.5 * 0.5;
   }
 }
 
@@ -449,8 +519,8 @@ extern "C" int vpb_lateral_init(vpb_lateral_state* state, void* stream) {
 }
 
 extern "C" int vpb_lateral_update(const float* masks, int H, int W, int img_w, int img_h, float smoothing,
-                                  const double* homography, vpb_lateral_state* state, vpb_lateral_out* out,
-                                  void* stream) {
+                                  const double* homography, double autosteer_steering_rad,
+                                  vpb_lateral_state* state, vpb_lateral_out* out, void* stream) {
   if (!masks || !state || !out || H < 41 || H > vpb::kMaxH || W < 2 || W > vpb::kMaxWords * 32 || img_w <= 0 || img_h <= 0) {
     vpb_set_error("lateral: need masks [3][H<=128][W<=256] (H >= 41), state and out");
     return VPB_ERR_ARG;
@@ -460,7 +530,7 @@ extern "C" int vpb_lateral_update(const float* masks, int H, int W, int img_w, i
                                1.85824549e-14,  -1.28170839e+00, 8.63871455e+02,
                                2.95628463e-17,  -1.76125061e-03, 1.00000000e+00};
   vpb::LatParams p;
-  p.H = H; p.W = W; p.smoothing = smoothing;
+  p.H = H; p.W = W; p.smoothing = smoothing; p.steering = autosteer_steering_rad;
   p.sx = static_cast<double>(img_w) / W; p.sy = static_cast<double>(img_h) / H;
   for (int k = 0; k < 9; ++k) p.Hm[k] = homography ? homography[k] : kH[k];
   vpb::inv3(p.Hm, p.Hi);

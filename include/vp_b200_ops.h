@@ -182,7 +182,10 @@ int vpb_bayes_fuse(double* state, const double* meas, int n_meas, void* stream);
  * 30 points else 2 — its RANSAC loop can never replace the all-points inlier set —, temporal smoothing)
  * followed by LaneTracker::update (src/lane_tracking/lane_tracking.cpp:36-300: BEV warp of the fitted
  * lines sampled every 5 px, lane-width history / recovery of a missing line, curve parameters in both
- * views).  Coefficient vectors are the reference's 6-vectors [c3, c2, c1, c0, min_y, max_y].
+ * views) and, when the BEV lines are valid, PathFinder::update (src/path_planning/path_finder.cpp:48-181:
+ * BEV pixels -> metres (main.cpp:333-357), fitQuadPoly (poly_fit.cpp:36-75), measurement vector,
+ * Estimator predict/update (estimator.cpp:15-74); the predict step's unseeded +-1e-5 mean jitter is 0).
+ * Coefficient vectors are the reference's 6-vectors [c3, c2, c1, c0, min_y, max_y].
  * Both structs live in DEVICE memory; the state persists from frame to frame. */
 typedef struct {
   double prev_left[6], prev_right[6];      /* LaneFilter::prev_*_fit (lane_filter.hpp:100-101)        */
@@ -190,6 +193,7 @@ typedef struct {
   double last_valid_bev_width;             /* LaneTracker (lane_tracking.hpp:86-87), 180.0 initially  */
   int has_valid_width_history;
   int reserved_;
+  double pf_state[14][2];                  /* PathFinder's Estimator state (mean, variance), path_finder.cpp:20-45 */
 } vpb_lateral_state;
 typedef struct {
   double left_coeffs[6], right_coeffs[6], center_coeffs[6];            /* LaneSegmentation (model space) */
@@ -202,16 +206,23 @@ typedef struct {
   int filt_left_valid, filt_right_valid;   /* LaneFilter produced a fit this frame                         */
   int left_start[2], right_start[2];       /* (x, y) of the ROI start points, -1 if none                   */
   int n_left_pts, n_right_pts;             /* points collected by the sliding windows                       */
+  /* PathFinderOutput (path_finder.hpp) — filled when bev_valid (main.cpp:565-577) */
+  double pf_left_coeff[3], pf_right_coeff[3];   /* fitQuadPoly in metres (NaN x3 with <= 2 points)          */
+  double pf_left_cte, pf_left_yaw_error, pf_right_cte, pf_right_yaw_error;
+  double pf_cte, pf_yaw_error, pf_curvature, pf_lane_width;
+  double pf_cte_variance, pf_yaw_variance, pf_curv_variance, pf_lane_width_variance;
+  int pf_fused_valid, pf_ran;
 } vpb_lateral_out;
 /* LaneFilter::reset + LaneTracker defaults */
 int vpb_lateral_init(vpb_lateral_state* state_dev, void* stream);
 /* masks: device float [3][H][W] (ego_left, ego_right, other_lanes; the output of vpb_lane_masks),
  * H <= 128 (>= 41), W <= 256; img_w x img_h = size of the source frame the homography refers to;
  * homography: host pointer to 9 doubles (orig -> BEV) or NULL for the reference's matrix
- * (lane_tracking.hpp:75-79). */
+ * (lane_tracking.hpp:75-79); autosteer_steering_rad: the steering value PathFinder takes as its
+ * curvature measurement (main.cpp:577). */
 int vpb_lateral_update(const float* masks, int H, int W, int img_w, int img_h, float smoothing,
-                       const double* homography, vpb_lateral_state* state_dev, vpb_lateral_out* out_dev,
-                       void* stream);
+                       const double* homography, double autosteer_steering_rad,
+                       vpb_lateral_state* state_dev, vpb_lateral_out* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

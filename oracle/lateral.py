@@ -302,6 +302,8 @@ class TrackOut:
     bev_center: Optional[np.ndarray] = None
     width_px: float = 0.0
     bev_valid: bool = False
+    bev_left_pts: Optional[np.ndarray] = None     # BEVVisuals.bev_left_pts / bev_right_pts (after recovery)
+    bev_right_pts: Optional[np.ndarray] = None
 
 
 class LaneTracker:
@@ -366,7 +368,49 @@ class LaneTracker:
             o.curvature = curvature(o.center, 79.0)
             o.width_px = self.width
             o.bev_valid = True
+            o.bev_left_pts, o.bev_right_pts = lb, rb
         return o
+
+
+# ----------------------------------------------------------------------------------------- PathFinder
+def pixels_to_meters(px: np.ndarray) -> np.ndarray:
+    """transformPixelsToMeters (production_release/main.cpp:333-357): 640 px = 40 m, vehicle at (320, 640);
+    double arithmetic on the float pixel coordinates, stored as float."""
+    px = np.asarray(px, dtype=np.float32).reshape(-1, 2)
+    scale = 40.0 / 640.0
+    return np.stack([(px[:, 0].astype(np.float64) - 320.0) * scale,
+                     (640.0 - px[:, 1].astype(np.float64)) * scale], axis=1).astype(np.float32)
+
+
+class PathFinder:
+    """PathFinder::update (src/path_planning/path_finder.cpp:48-181) on the LaneTracker's BEV points.
+    The predict step's process MEAN is drawn from an unseeded U(-1e-5, 1e-5) in the reference
+    (path_finder.cpp:59-68); it is taken as 0 here and in the device kernel (five orders of magnitude below
+    the measurement noise), the process variance PROC_SD^2 = 0.25 is added as in the reference."""
+
+    def __init__(self, default_lane_width: float = 4.0):
+        from . import post
+        self._post = post
+        self.default_width = default_lane_width
+        self.state = post.initial_state(default_lane_width)
+
+    def update(self, left_px: np.ndarray, right_px: np.ndarray, steering_rad: float) -> dict:
+        post = self._post
+        self.state[:, 1] += 0.5 * 0.5                                   # Estimator::predict
+        lm, rm = pixels_to_meters(left_px), pixels_to_meters(right_px)
+        lc = post.polyfit(lm[:, 0], lm[:, 1], 2) if len(lm) > 2 else np.full(3, np.nan)
+        rc = post.polyfit(rm[:, 0], rm[:, 1], 2) if len(rm) > 2 else np.full(3, np.nan)
+        width = self.state[12, 0]
+        meas = post.pathfinder_measurement(lc, rc, steering_rad, width, self.default_width)
+        self.state = post.estimator_update(self.state, meas)
+        l_cte, l_yaw = post.fitted_curve(lc)
+        r_cte, r_yaw = post.fitted_curve(rc)
+        st = self.state
+        return {"left_coeff": lc, "right_coeff": rc, "left_cte": l_cte, "left_yaw_error": l_yaw,
+                "right_cte": r_cte, "right_yaw_error": r_yaw, "cte": st[3, 0], "yaw_error": st[7, 0],
+                "curvature": steering_rad, "lane_width": st[12, 0], "cte_variance": st[3, 1],
+                "yaw_variance": st[7, 1], "curv_variance": st[11, 1], "lane_width_variance": st[12, 1],
+                "fused_valid": not (math.isnan(st[3, 0]) or math.isnan(st[7, 0]) or math.isnan(steering_rad))}
 
 
 def synth_lane_masks(seed: int, H: int = 80, W: int = 160, drop_left=False, drop_right=False, noise=0.01):

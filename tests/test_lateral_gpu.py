@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 RT, AT = 1e-9, 1e-9
 
 
-def _check(dev, o, tr, tracker):
+def _check(dev, o, tr, tracker, po=None):
     assert list(dev["left_start"]) == list(o.left_start) and list(dev["right_start"]) == list(o.right_start)
     assert dev["n_left_pts"] == o.n_left and dev["n_right_pts"] == o.n_right
     assert bool(dev["filt_left_valid"]) == (o.left is not None) and bool(dev["filt_right_valid"]) == (o.right is not None)
@@ -33,6 +33,14 @@ def _check(dev, o, tr, tracker):
                      ("bev_curvature", tr.bev_curvature)):
             np.testing.assert_allclose(dev[k], v, rtol=1e-7, atol=1e-7)
         np.testing.assert_allclose(dev["last_valid_width_pixels"], tracker.width, rtol=RT, atol=AT)
+    assert bool(dev["pf_ran"]) == (po is not None)
+    if po is not None:     # PathFinder (metric fits of ~100-point lines: 1e-7; Bayes state follows)
+        np.testing.assert_allclose(dev["pf_left_coeff"], po["left_coeff"], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(dev["pf_right_coeff"], po["right_coeff"], rtol=1e-6, atol=1e-8)
+        for k in ("left_cte", "left_yaw_error", "right_cte", "right_yaw_error", "cte", "yaw_error", "curvature",
+                  "lane_width", "cte_variance", "yaw_variance", "curv_variance", "lane_width_variance"):
+            np.testing.assert_allclose(dev["pf_" + k], po[k], rtol=1e-7, atol=1e-8, err_msg=k)
+        assert bool(dev["pf_fused_valid"]) == po["fused_valid"]
 
 
 @pytest.mark.parametrize("seed0", [100, 200, 300, 4000])
@@ -41,18 +49,22 @@ def test_sequence_with_dropouts_matches_oracle(seed0):
     the recovery of a dropped left / right line (lane_tracking.cpp:129-207)."""
     from autoware_vision_pilot_b200.lateral import LateralPostProcess
     post = LateralPostProcess(image_size=(1920, 1080))
-    f, t = LT.LaneFilter(), LT.LaneTracker()
+    f, t, pf = LT.LaneFilter(), LT.LaneTracker(), LT.PathFinder()
     for k in range(12):
         m = LT.synth_lane_masks(seed0 + k, drop_left=(k in (3, 6, 7)), drop_right=(k in (5, 9)))
         o = f.update(m)
         tr = t.update(o.left, o.right)
-        dev = post.update(torch.from_numpy(m).cuda())
-        _check(dev, o, tr, t)
+        steer = 0.02 * (k - 5)
+        po = pf.update(tr.bev_left_pts, tr.bev_right_pts, steer) if tr.bev_valid else None
+        dev = post.update(torch.from_numpy(m).cuda(), autosteer_steering_rad=steer)
+        _check(dev, o, tr, t, po)
     post.reset()
     f2, t2 = LT.LaneFilter(), LT.LaneTracker()
     m = LT.synth_lane_masks(seed0)
     o = f2.update(m)
-    _check(post.update(torch.from_numpy(m).cuda()), o, t2.update(o.left, o.right), t2)
+    tr = t2.update(o.left, o.right)
+    po = LT.PathFinder().update(tr.bev_left_pts, tr.bev_right_pts, 0.0) if tr.bev_valid else None
+    _check(post.update(torch.from_numpy(m).cuda()), o, tr, t2, po)
 
 
 def test_edge_cases_empty_single_row_and_few_points():
@@ -60,7 +72,7 @@ def test_edge_cases_empty_single_row_and_few_points():
     solution); fewer than 4 points (fit invalid, previous fit kept); noise only."""
     from autoware_vision_pilot_b200.lateral import LateralPostProcess
     post = LateralPostProcess()
-    f, t = LT.LaneFilter(), LT.LaneTracker()
+    f, t, pf = LT.LaneFilter(), LT.LaneTracker(), LT.PathFinder()
     frames = []
     frames.append(np.zeros((3, 80, 160), np.float32))
     m = np.zeros((3, 80, 160), np.float32); m[0, 70, 40:52] = 1; m[1, 70, 100:140] = 1          # single rows
@@ -78,7 +90,8 @@ def test_edge_cases_empty_single_row_and_few_points():
     for m in frames:
         o = f.update(m)
         tr = t.update(o.left, o.right)
-        _check(post.update(torch.from_numpy(m).cuda()), o, tr, t)
+        po = pf.update(tr.bev_left_pts, tr.bev_right_pts, 0.1) if tr.bev_valid else None
+        _check(post.update(torch.from_numpy(m).cuda(), autosteer_steering_rad=0.1), o, tr, t, po)
 
 
 def test_runs_on_the_engine_output_without_leaving_the_device(tmp_path):
@@ -104,4 +117,6 @@ def test_runs_on_the_engine_output_without_leaving_the_device(tmp_path):
     m = (eng.raw(0) > 0.0).astype(np.float32)
     f, t = LT.LaneFilter(), LT.LaneTracker()
     o = f.update(m)
-    _check(dev, o, t.update(o.left, o.right), t)
+    tr = t.update(o.left, o.right)
+    po = LT.PathFinder().update(tr.bev_left_pts, tr.bev_right_pts, 0.0) if tr.bev_valid else None
+    _check(dev, o, tr, t, po)
