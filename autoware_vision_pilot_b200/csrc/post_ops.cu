@@ -13,6 +13,7 @@
 // and the lane geometry (the reference does cudaMalloc + H2D + kernel + D2H per frame,
 // cuda_visualization_kernels.cu:100-129).
 #include "common.cuh"
+#include <cstring>
 #include "ops_internal.h"
 #include <cmath>
 
@@ -89,6 +90,63 @@ __global__ void resize_linear_f32_kernel(const float* __restrict__ src, int sh, 
   const float h0 = __fadd_rn(__fmul_rn(r0[sx], a0), __fmul_rn(r0[sx1], a1));
   const float h1 = __fadd_rn(__fmul_rn(r1[sx], a0), __fmul_rn(r1[sx1], a1));
   dst[static_cast<size_t>(y) * dw + x] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+}
+
+// ------------------------------------------------------------------ mask overlay on the camera frame
+// MasksVisualizationEngine::visualize (middleware_recipes/common/visualizers/masks_visualization_engine.cpp
+// :11-38) in ONE pass over the frame: createColorMask (:40-60) -> cv::resize INTER_NEAREST to the frame
+// size -> cv::addWeighted(color, 0.5, frame, 0.5, 0).  The reference materialises a colour image at mask
+// size, a resized colour image and the blend (3 frame-sized passes on the CPU); here every output pixel
+// looks up its nearest mask pixel, maps it through the 3-entry palette and blends.  addWeighted on 8U
+// rounds half to even (pinned against cv2 over all 65 536 (colour, pixel) pairs in
+// tests/test_oracle_post.py): (c + o) / 2 with ties to the even integer.
+// HBM-bound: reads 3*H*W (frame) + the small mask, writes 3*H*W.
+struct VizLut { uint8_t bgr[4][3]; };   // palette index 3 = "no colour" (0,0,0)
+
+__device__ __forceinline__ int viz_class(int viz_type, int m) {
+  if (viz_type == VPB_VIZ_SCENE) return (m >= 1) ? 0 : 3;                       // inRange(mask, 1, 255) -> red
+  if (viz_type == VPB_VIZ_DOMAIN) return m == 0 ? 0 : (m == 255 ? 1 : 3);
+  return m <= 2 ? m : 3;                                                         // egolanes ids 0/1/2, 255 = none
+}
+__device__ __forceinline__ uint32_t blend_half_even(uint32_t c, uint32_t o) {
+  const uint32_t s = c + o, h = s >> 1;
+  return h + ((s & 1u) & (h & 1u));
+}
+
+__global__ void __launch_bounds__(256) visualize_mask_kernel(const uint8_t* __restrict__ mask, int mh, int mw,
+                                                             int viz_type, VizLut lut,
+                                                             const uint8_t* __restrict__ frame, int h, int w,
+                                                             int stride, uint8_t* __restrict__ out, int out_stride,
+                                                             double ify, double ifx) {
+  // one thread = 4 consecutive pixels = 12 bytes = three aligned 32-bit words (when the rows allow it)
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  if (x4 >= w) return;
+  const int sy = min(static_cast<int>(floor(y * ify)), mh - 1);
+  const uint8_t* mrow = mask + static_cast<size_t>(sy) * mw;
+  const uint8_t* frow = frame + static_cast<size_t>(y) * stride + static_cast<size_t>(x4) * 3;
+  uint8_t* orow = out + static_cast<size_t>(y) * out_stride + static_cast<size_t>(x4) * 3;
+  const bool vec = (x4 + 4 <= w) && ((reinterpret_cast<uintptr_t>(frow) & 3u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(orow) & 3u) == 0);
+  uint8_t px[12];
+  if (vec) {
+    const uint32_t* f32 = reinterpret_cast<const uint32_t*>(frow);
+    const uint32_t a = __ldg(f32), b = __ldg(f32 + 1), c = __ldg(f32 + 2);
+    *reinterpret_cast<uint32_t*>(px) = a; *reinterpret_cast<uint32_t*>(px + 4) = b; *reinterpret_cast<uint32_t*>(px + 8) = c;
+  }
+  const int npx = min(4, w - x4);
+  for (int i = 0; i < npx; ++i) {
+    const int sx = min(static_cast<int>(floor((x4 + i) * ifx)), mw - 1);
+    const int k = viz_class(viz_type, mrow[sx]);
+    for (int ch = 0; ch < 3; ++ch) {
+      const uint32_t o = vec ? px[3 * i + ch] : frow[3 * i + ch];
+      const uint8_t r = static_cast<uint8_t>(blend_half_even(lut.bgr[k][ch], o));
+      if (vec) px[3 * i + ch] = r; else orow[3 * i + ch] = r;
+    }
+  }
+  if (vec) {
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(orow);
+    o32[0] = *reinterpret_cast<uint32_t*>(px); o32[1] = *reinterpret_cast<uint32_t*>(px + 4); o32[2] = *reinterpret_cast<uint32_t*>(px + 8);
+  }
 }
 
 // ------------------------------------------------------------------ lane poly-fit (fp64)
@@ -225,6 +283,27 @@ extern "C" int vpb_resize_linear_f32(const float* src, int sh, int sw, float* ds
   dim3 grid((dw + 255) / 256, dh);
   resize_linear_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, sh, sw, dst, dh, dw, static_cast<double>(sh) / dh, static_cast<double>(sw) / dw);
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}
+extern "C" int vpb_visualize_mask(const uint8_t* mask, int mh, int mw, int viz_type, const uint8_t* frame_bgr, int h, int w,
+                                  int stride, uint8_t* out, int out_stride, void* stream) {
+  if (!mask || !frame_bgr || !out || mh <= 0 || mw <= 0 || h <= 0 || w <= 0 || stride < 3 * w || out_stride < 3 * w ||
+      viz_type < VPB_VIZ_SCENE || viz_type > VPB_VIZ_EGOLANES) {
+    vpb_set_error("visualize_mask: bad arguments");
+    return VPB_ERR_ARG;
+  }
+  // palettes of createColorMask (masks_visualization_engine.cpp:40-60), BGR
+  static const uint8_t kPal[3][4][3] = {
+      {{0, 0, 255}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}},                 // scene: foreground red
+      {{255, 93, 61}, {145, 28, 255}, {0, 0, 0}, {0, 0, 0}},          // domain: 0 orange, 255 purple
+      {{255, 0, 0}, {255, 0, 200}, {0, 153, 0}, {0, 0, 0}}};          // egolanes: left, right, other
+  vpb::VizLut lut;
+  memcpy(lut.bgr, kPal[viz_type], sizeof(lut.bgr));
+  const double ifx = 1.0 / (static_cast<double>(w) / mw), ify = 1.0 / (static_cast<double>(h) / mh);
+  dim3 grid(((w + 3) / 4 + 255) / 256, h);
+  vpb::visualize_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, mh, mw, viz_type, lut, frame_bgr, h,
+                                                                                 w, stride, out, out_stride, ify, ifx);
   VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
 }

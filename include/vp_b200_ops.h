@@ -163,6 +163,14 @@ int vpb_lane_masks(const float* raw, int n, float threshold, float* out, void* s
  * (run_model_node.cpp:177) and INTER_LINEAR on the CV_32FC1 depth map (run_model_node.cpp:96-104) */
 int vpb_resize_nearest_u8(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw, void* stream);
 int vpb_resize_linear_f32(const float* src, int sh, int sw, float* dst, int dh, int dw, void* stream);
+/* MasksVisualizationEngine::visualize (middleware_recipes/common/visualizers/masks_visualization_engine.cpp
+ * :11-38) fused into one pass: createColorMask (:40-60, viz_type "scene" | "domain" | "egolanes") ->
+ * cv::resize INTER_NEAREST to the frame size -> cv::addWeighted(color, 0.5, frame, 0.5, 0) (8U, ties to
+ * even).  mask: device uint8 [mh][mw] (vpb_mask255 / vpb_egolanes_ids output), frame_bgr / out: device
+ * uint8 [h][w][3] with row strides in bytes. */
+enum { VPB_VIZ_SCENE = 0, VPB_VIZ_DOMAIN = 1, VPB_VIZ_EGOLANES = 2 };
+int vpb_visualize_mask(const uint8_t* mask, int mh, int mw, int viz_type, const uint8_t* frame_bgr, int h,
+                       int w, int stride, uint8_t* out, int out_stride, void* stream);
 /* Lane poly-fit least squares, fp64, one warp per point set (set i = points offsets[i]..offsets[i+1]):
  * x = c0*y^order + ... (highest power first), order 1..3 ->  coeffs[set][4] (unused slots 0; NaN if the
  * set has <= order points), yrange[set][2] = (min_y, max_y) (may be NULL).

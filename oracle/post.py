@@ -14,6 +14,9 @@
 * `Estimator::update` (production_release/src/path_planning/estimator.cpp:24-74) with PathFinder's
   fusion groups (path_finder.cpp:24-30) and the measurement construction of
   PathFinder::update (path_finder.cpp:97-157).
+* mask overlay — `MasksVisualizationEngine::visualize`
+  (middleware_recipes/common/visualizers/masks_visualization_engine.cpp:11-60): palette, nearest resize to
+  the frame size, cv::addWeighted(color, 0.5, frame, 0.5, 0) (8U: ties to even), pinned against cv2.
 """
 from __future__ import annotations
 
@@ -136,3 +139,37 @@ def initial_state(default_width: float = 4.0) -> np.ndarray:
     st = np.tile(np.array([0.0, 1e3]), (STATE_DIM, 1))
     st[12] = (default_width, 0.25)
     return st
+
+
+VIZ_PALETTES = {   # createColorMask (masks_visualization_engine.cpp:40-60), BGR
+    "scene": {"range": (1, 255), "color": (0, 0, 255)},
+    "domain": {0: (255, 93, 61), 255: (145, 28, 255)},
+    "egolanes": {0: (255, 0, 0), 1: (255, 0, 200), 2: (0, 153, 0)},
+}
+
+
+def color_mask(mask: np.ndarray, viz_type: str) -> np.ndarray:
+    out = np.zeros(mask.shape + (3,), dtype=np.uint8)
+    pal = VIZ_PALETTES[viz_type]
+    if viz_type == "scene":
+        lo, hi = pal["range"]
+        out[(mask >= lo) & (mask <= hi)] = pal["color"]
+    else:
+        for v, c in pal.items():
+            out[mask == v] = c
+    return out
+
+
+def add_weighted_half(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """cv::addWeighted(a, 0.5, b, 0.5, 0) on 8U: (a + b) / 2 rounded half to even."""
+    s = a.astype(np.int32) + b.astype(np.int32)
+    h = s >> 1
+    return (h + ((s & 1) & (h & 1))).astype(np.uint8)
+
+
+def visualize_mask(mask: np.ndarray, frame_bgr: np.ndarray, viz_type: str) -> np.ndarray:
+    h, w = frame_bgr.shape[:2]
+    cm = color_mask(mask, viz_type)
+    if cm.shape[:2] != (h, w):
+        cm = np.stack([resize_nearest(cm[..., c], w, h) for c in range(3)], axis=2)
+    return add_weighted_half(cm, frame_bgr)

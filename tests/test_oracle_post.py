@@ -54,3 +54,28 @@ def test_estimator_update_properties():
     # both lanes missing -> default width measurement (path_finder.cpp:141-143)
     nan3 = [float("nan")] * 3
     assert post.pathfinder_measurement(nan3, nan3, 0.0, 3.5)[12, 0] == 4.0
+
+
+@pytest.mark.parametrize("viz", ["scene", "domain", "egolanes"])
+def test_visualize_mask_matches_cv2_pipeline(viz):
+    """createColorMask -> cv::resize(INTER_NEAREST) -> cv::addWeighted as the reference composes them
+    (masks_visualization_engine.cpp:11-38), against the oracle's single-expression restatement."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    vals = {"scene": [0, 255], "domain": [0, 255, 7], "egolanes": [0, 1, 2, 255]}[viz]
+    mask = rng.choice(vals, size=(320, 640)).astype(np.uint8)
+    frame = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    cm = post.color_mask(mask, viz)
+    ref_cm = np.zeros((320, 640, 3), np.uint8)
+    if viz == "scene":
+        ref_cm[cv2.inRange(mask, 1, 255) > 0] = (0, 0, 255)
+    elif viz == "domain":
+        ref_cm[mask == 0] = (255, 93, 61); ref_cm[mask == 255] = (145, 28, 255)
+    else:
+        ref_cm[mask == 0] = (255, 0, 0); ref_cm[mask == 1] = (255, 0, 200); ref_cm[mask == 2] = (0, 153, 0)
+    assert np.array_equal(cm, ref_cm)
+    ref = cv2.addWeighted(cv2.resize(ref_cm, (1920, 1080), interpolation=cv2.INTER_NEAREST), 0.5, frame, 0.5, 0.0)
+    assert np.array_equal(post.visualize_mask(mask, frame, viz), ref)
+    a = np.arange(256, dtype=np.uint8).reshape(-1, 1).repeat(256, 1)
+    b = a.T.copy()
+    assert np.array_equal(post.add_weighted_half(a, b), cv2.addWeighted(a, 0.5, b, 0.5, 0.0))

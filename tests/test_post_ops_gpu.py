@@ -123,3 +123,24 @@ def test_bayes_fusion_over_eight_cameras():
     L.check(lib.vpb_bayes_fuse(ds.data_ptr(), dm.data_ptr(), 8, None), "fuse")
     got = ds.cpu().numpy()
     assert np.allclose(got, ref, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("viz,code", [("scene", 0), ("domain", 1), ("egolanes", 2)])
+@pytest.mark.parametrize("h,w", [(1080, 1920), (321, 643)])
+def test_visualize_mask_overlay_is_bit_exact(viz, code, h, w):
+    """vpb_visualize_mask (palette + nearest resize + half/half blend in one pass) == the reference's
+    three-step composition restated in oracle/post.py (pinned against cv2 on the CPU)."""
+    lib = L.lib()
+    lib.vpb_visualize_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(h + code)
+    vals = {"scene": [0, 255], "domain": [0, 255, 9], "egolanes": [0, 1, 2, 255]}[viz]
+    mask = rng.choice(vals, size=(320, 640)).astype(np.uint8)
+    frame = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    dm, df = torch.from_numpy(mask).cuda(), torch.from_numpy(frame).cuda()
+    out = torch.empty_like(df)
+    L.check(lib.vpb_visualize_mask(dm.data_ptr(), 320, 640, code, df.data_ptr(), h, w, 3 * w, out.data_ptr(), 3 * w,
+                                   None), "vpb_visualize_mask")
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), post.visualize_mask(mask, frame, viz))
+    assert lib.vpb_visualize_mask(dm.data_ptr(), 320, 640, 7, df.data_ptr(), h, w, 3 * w, out.data_ptr(), 3 * w, None) != 0
