@@ -77,6 +77,13 @@ public:
     if (!ran_) throw std::runtime_error("Inference has not been run yet. Call inference() first.");
     return out_.raw_host;
   }
+  // Not in the reference interface: the same tensor while it is still in HBM, for the on-device
+  // lateral post-process (vpb_lane_masks + vpb_lateral_update).
+  const float * rawDevice() const
+  {
+    if (!ran_) throw std::runtime_error("Inference has not been run yet. Call inference() first.");
+    return out_.raw_dev;
+  }
   std::vector<int64_t> getTensorShape() const
   {
     return {1, static_cast<int64_t>(out_.channels), static_cast<int64_t>(out_.height), static_cast<int64_t>(out_.width)};

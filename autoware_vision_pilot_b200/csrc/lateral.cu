@@ -29,11 +29,12 @@ static constexpr int kMaxGen = 256;                   // points generated from o
 
 struct LatShared {
   uint32_t bits[3][kMaxH][kMaxWords];
-  float px[kMaxPts], py[kMaxPts];      // current point list (x, y)
+  uint8_t px[2][kMaxPts], py[2][kMaxPts];   // point list (x, y) of the left / right line (x < 256, y < 128)
+  double fit[2][6];                         // LaneFilter result per side (after smoothing)
+  int fit_valid[2], start[2][2], npts[2];
   float ax[kMaxGen], ay[kMaxGen];      // BEV points of the left line
   float bx[kMaxGen], by[kMaxGen];      // BEV points of the right line
   float cx[kMaxGen], cy[kMaxGen];      // scratch (centre line / recovered line)
-  int n_pts;
 };
 
 __device__ __forceinline__ bool bit_at(const LatShared& s, int ch, int y, int x) {
@@ -50,7 +51,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // (fewer distinct y than unknowns — possible for the integer pixel rows of LaneFilter) gets the
 // MINIMUM-NORM solution, which is what cv::solve(DECOMP_SVD) returns (lane_filter.cpp:96-101).
 // `integer_y`: y values are small non-negative integers (distinct count via a bit mask).
-__device__ void warp_fit(const float* xs, const float* ys, int n, int order, bool integer_y, double c[3],
+template <class T>
+__device__ void warp_fit(const T* xs, const T* ys, int n, int order, bool integer_y, double c[3],
                          double* ymin_out, double* ymax_out) {
   const int lane = threadIdx.x & 31;
   double ymin = 1e300, ymax = -1e300;
@@ -147,10 +149,26 @@ __device__ void warp_fit(const float* xs, const float* ys, int n, int order, boo
   c[0] = a[0] - a1 * mid + a2 * mid * mid;
 }
 
-// slidingWindowSearch (lane_filter.cpp:376-590): appends to s.px / s.py in the reference's push order.
-__device__ void sliding_search(LatShared& s, int H, int W, int sx0, int sy0, bool is_left) {
+// `ww` (<= 12) mask bits of row `y` starting at column x_lo
+__device__ __forceinline__ uint32_t row_field(const LatShared& s, int ch, int y, int x_lo, int ww) {
+  const int w0 = x_lo >> 5;
+  const uint64_t lo = s.bits[ch][y][w0];
+  const uint64_t hi = (w0 + 1 < kMaxWords) ? s.bits[ch][y][w0 + 1] : 0u;
+  return static_cast<uint32_t>(((hi << 32) | lo) >> (x_lo & 31)) & ((1u << ww) - 1u);
+}
+// sum of the positions of the set bits (bits < 2^16): binary decomposition of the position
+__device__ __forceinline__ int pos_sum(uint32_t b) {
+  return __popc(b & 0xAAAAu) + 2 * __popc(b & 0xCCCCu) + 4 * __popc(b & 0xF0F0u) + 8 * __popc(b & 0xFF00u);
+}
+
+// slidingWindowSearch (lane_filter.cpp:376-590) by one warp: lanes 0..3 each own one row of the (<= 4 x 12)
+// window as a bit field, counts / centroid sums are a handful of popcounts, points are appended in the
+// reference's push order (row-major inside a window).  Returns the number of points (capped at kMaxPts).
+__device__ int sliding_search(const LatShared& s, uint8_t* px, uint8_t* py, int H, int W, int sx0, int sy0,
+                              bool is_left) {
   const int lane = threadIdx.x & 31;
   const int ch_ego = is_left ? 0 : 1;
+  int n_pts = 0;
   for (int dirpass = 0; dirpass < 2; ++dirpass) {
     const int step_y = dirpass == 0 ? -1 : 1;
     int cx = sx0, cy = sy0;
@@ -167,41 +185,35 @@ __device__ void sliding_search(LatShared& s, int H, int W, int sx0, int sy0, boo
       if (step_y < 0) { y_lo = max(0, cy - 4); y_hi = cy; } else { y_lo = cy; y_hi = min(H, cy + 4); }
       const int x_lo = max(0, cx - cw), x_hi = min(W, cx + cw);
       const bool strict = cy < 40;
-      const int ww = x_hi - x_lo, np = ww * (y_hi - y_lo);          // <= 12 x 4 pixels, row-major
-      // pass 1: count ego / other pixels
-      int n_ego = 0, n_oth = 0;
-      for (int base = 0; base < np; base += 32) {
-        const int i = base + lane;
-        bool e = false, o = false;
-        if (i < np) {
-          const int y = y_lo + i / ww, x = x_lo + i % ww;
-          e = bit_at(s, ch_ego, y, x);
-          o = !strict && bit_at(s, 2, y, x);
-        }
-        n_ego += __popc(__ballot_sync(0xffffffffu, e));
-        n_oth += __popc(__ballot_sync(0xffffffffu, o));
+      const int ww = x_hi - x_lo, rows = y_hi - y_lo;
+      const int y = y_lo + lane;
+      uint32_t eb = 0, ob = 0;
+      if (lane < rows && ww > 0) {
+        eb = row_field(s, ch_ego, y, x_lo, ww);
+        if (!strict) ob = row_field(s, 2, y, x_lo, ww);
       }
-      const int pick = n_ego >= 3 ? ch_ego : (n_oth >= 3 ? 2 : -1);
-      if (pick >= 0) {
-        // pass 2: append the chosen bucket in scan order, integer sums for the centroid
-        long sum_x = 0, sum_y = 0;
-        int cnt = 0;
-        for (int base = 0; base < np; base += 32) {
-          const int i = base + lane;
-          bool f = false;
-          int y = 0, x = 0;
-          if (i < np) { y = y_lo + i / ww; x = x_lo + i % ww; f = bit_at(s, pick, y, x); }
-          const uint32_t bal = __ballot_sync(0xffffffffu, f);
-          const int pos = s.n_pts + cnt + __popc(bal & ((1u << lane) - 1u));
-          if (f && pos < kMaxPts) { s.px[pos] = static_cast<float>(x); s.py[pos] = static_cast<float>(y); }
-          long lx = f ? x : 0, ly = f ? y : 0;
-          for (int o = 16; o > 0; o >>= 1) { lx += __shfl_xor_sync(0xffffffffu, lx, o); ly += __shfl_xor_sync(0xffffffffu, ly, o); }
-          sum_x += lx; sum_y += ly;
-          cnt += __popc(bal);
+      // per-row counts of lanes 0..3 -> window totals (every lane gets the same values)
+      const int e0 = __shfl_sync(0xffffffffu, __popc(eb), 0), e1 = __shfl_sync(0xffffffffu, __popc(eb), 1),
+                e2 = __shfl_sync(0xffffffffu, __popc(eb), 2), e3 = __shfl_sync(0xffffffffu, __popc(eb), 3);
+      const int o0 = __shfl_sync(0xffffffffu, __popc(ob), 0), o1 = __shfl_sync(0xffffffffu, __popc(ob), 1),
+                o2 = __shfl_sync(0xffffffffu, __popc(ob), 2), o3 = __shfl_sync(0xffffffffu, __popc(ob), 3);
+      const int n_ego = e0 + e1 + e2 + e3, n_oth = o0 + o1 + o2 + o3;
+      const bool use_ego = n_ego >= 3, use_oth = !use_ego && n_oth >= 3;
+      if (use_ego || use_oth) {
+        const uint32_t bits = use_ego ? eb : ob;
+        const int c0 = use_ego ? e0 : o0, c1 = use_ego ? e1 : o1, c2 = use_ego ? e2 : o2;
+        const int cnt = use_ego ? n_ego : n_oth;
+        const int my = __popc(bits);
+        int sxr = my * x_lo + pos_sum(bits), syr = my * y;     // this row's coordinate sums
+        sxr += __shfl_xor_sync(0xffffffffu, sxr, 1); sxr += __shfl_xor_sync(0xffffffffu, sxr, 2);
+        syr += __shfl_xor_sync(0xffffffffu, syr, 1); syr += __shfl_xor_sync(0xffffffffu, syr, 2);
+        const long sum_x = __shfl_sync(0xffffffffu, sxr, 0), sum_y = __shfl_sync(0xffffffffu, syr, 0);
+        int pos = n_pts + (lane > 0 ? c0 : 0) + (lane > 1 ? c1 : 0) + (lane > 2 ? c2 : 0);
+        for (uint32_t b = bits; b; b &= b - 1) {
+          if (pos < kMaxPts) { px[pos] = static_cast<uint8_t>(x_lo + __ffs(b) - 1); py[pos] = static_cast<uint8_t>(y); }
+          ++pos;
         }
-        __syncwarp();
-        if (lane == 0) s.n_pts = min(kMaxPts, s.n_pts + cnt);
-        __syncwarp();
+        n_pts = min(kMaxPts, n_pts + cnt);
         const float cxf = static_cast<float>(sum_x) / static_cast<float>(cnt);
         const float cyf = static_cast<float>(sum_y) / static_cast<float>(cnt);
         empty = 0;
@@ -220,6 +232,8 @@ __device__ void sliding_search(LatShared& s, int H, int W, int sx0, int sy0, boo
       if (step_y > 0 && cy <= y_lo + 1) cy += 4;
     }
   }
+  __syncwarp();
+  return n_pts;
 }
 
 struct LatParams {
@@ -303,51 +317,69 @@ __global__ void __launch_bounds__(256) lateral_kernel(const float* __restrict__ 
     s.bits[ch][y][w] = bitsv;
   }
   __syncthreads();
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // ---- findStartingPoints (lane_filter.cpp:325-370)
-  const int mid = W / 2;
-  int lsx = -1, lsy = -1, rsx = -1, rsy = -1;
-  for (int y = 79 < H ? 79 : H - 1; y >= 40 && lsx < 0; --y)
-    for (int x = mid - 1; x >= 0; --x)
-      if (bit_at(s, 0, y, x)) { lsx = x; lsy = y; break; }
-  for (int y = 79 < H ? 79 : H - 1; y >= 40 && rsx < 0; --y)
-    for (int x = mid; x < W; ++x)
-      if (bit_at(s, 1, y, x)) { rsx = x; rsy = y; break; }
-
-  double fit[2][6];
-  bool valid[2] = {false, false};
-  int npts[2] = {0, 0};
-  for (int side = 0; side < 2; ++side) {
-    const int sx0 = side == 0 ? lsx : rsx, sy0 = side == 0 ? lsy : rsy;
+  // ---- LaneFilter::update, the left line on warp 0 and the right line on warp 1 (independent until the
+  //      tracker): findStartingPoints (lane_filter.cpp:325-370) -> sliding windows -> fit -> smoothing
+  if (warp < 2) {
+    const int side = warp;
+    const int mid = W / 2;
+    int sx0 = -1, sy0 = -1;
+    for (int y = 79 < H ? 79 : H - 1; y >= 40 && sx0 < 0; --y) {
+      if (side == 0) {                       // largest x < mid with the ego-left bit set
+        for (int w = (mid - 1) >> 5; w >= 0 && sx0 < 0; --w) {
+          uint32_t v = s.bits[0][y][w];
+          const int top = mid - w * 32;      // columns >= mid are excluded
+          if (top < 32) v &= (1u << top) - 1u;
+          if (v) { sx0 = w * 32 + 31 - __clz(v); sy0 = y; }
+        }
+      } else {                               // smallest x >= mid with the ego-right bit set
+        for (int w = mid >> 5; w < words && sx0 < 0; ++w) {
+          uint32_t v = s.bits[1][y][w];
+          const int lowx = mid - w * 32;     // columns < mid are excluded
+          if (lowx > 0) v &= ~((1u << lowx) - 1u);
+          if (v) { sx0 = w * 32 + __ffs(v) - 1; sy0 = y; }
+        }
+      }
+    }
     double* prev = side == 0 ? st->prev_left : st->prev_right;
     int* prev_valid = side == 0 ? &st->prev_left_valid : &st->prev_right_valid;
+    int n = 0;
+    bool ok = false;
+    double cur[6] = {0, 0, 0, 0, 0, 0};
     if (sx0 < 0) {                                   // no detection: previous fit invalidated
       if (lane == 0) *prev_valid = 0;
-      continue;
+    } else {
+      n = sliding_search(s, s.px[side], s.py[side], H, W, sx0, sy0, side == 0);
+      if (n >= 4) {                                  // fitPoly (n < 4: invalid, previous fit kept)
+        const int order = n < 30 ? 1 : 2;
+        double c[3], ymin, ymax;
+        warp_fit(s.px[side], s.py[side], n, order, true, c, &ymin, &ymax);
+        cur[1] = c[2]; cur[2] = c[1]; cur[3] = c[0]; cur[4] = ymin; cur[5] = ymax;
+        if (*prev_valid) {                           // temporal smoothing, float factor promoted to double
+          const double a = static_cast<double>(p.smoothing), b = static_cast<double>(1.0f - p.smoothing);
+          for (int k = 0; k < 6; ++k) cur[k] = a * cur[k] + b * prev[k];
+        }
+        __syncwarp();
+        if (lane == 0) { for (int k = 0; k < 6; ++k) prev[k] = cur[k]; *prev_valid = 1; }
+        ok = true;
+      }
     }
-    if (lane == 0) s.n_pts = 0;
-    __syncwarp();
-    sliding_search(s, H, W, sx0, sy0, side == 0);
-    __syncwarp();
-    const int n = s.n_pts;
-    npts[side] = n;
-    if (n < 4) continue;                             // fitPoly: invalid, previous fit kept
-    const int order = n < 30 ? 1 : 2;
-    double c[3], ymin, ymax;
-    warp_fit(s.px, s.py, n, order, true, c, &ymin, &ymax);
-    double cur[6] = {0.0, c[2], c[1], c[0], ymin, ymax};
-    if (*prev_valid) {                               // temporal smoothing, float factor promoted to double
-      const double a = static_cast<double>(p.smoothing), b = static_cast<double>(1.0f - p.smoothing);
-      for (int k = 0; k < 6; ++k) cur[k] = a * cur[k] + b * prev[k];
+    if (lane == 0) {
+      for (int k = 0; k < 6; ++k) s.fit[side][k] = cur[k];
+      s.fit_valid[side] = ok; s.start[side][0] = sx0; s.start[side][1] = sy0; s.npts[side] = n;
     }
-    __syncwarp();
-    if (lane == 0) { for (int k = 0; k < 6; ++k) prev[k] = cur[k]; *prev_valid = 1; }
-    __syncwarp();
-    for (int k = 0; k < 6; ++k) fit[side][k] = cur[k];
-    valid[side] = true;
   }
+  __syncthreads();
+  if (warp != 0) return;
+  double fit[2][6];
+  bool valid[2];
+  int npts[2];
+  for (int sd = 0; sd < 2; ++sd) {
+    for (int k = 0; k < 6; ++k) fit[sd][k] = s.fit[sd][k];
+    valid[sd] = s.fit_valid[sd] != 0; npts[sd] = s.npts[sd];
+  }
+  const int lsx = s.start[0][0], lsy = s.start[0][1], rsx = s.start[1][0], rsy = s.start[1][1];
 
   // ---- LaneTracker::update (lane_tracking.cpp:36-300)
   double left6[6], right6[6];

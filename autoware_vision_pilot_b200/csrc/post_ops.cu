@@ -101,7 +101,7 @@ __global__ void resize_linear_f32_kernel(const float* __restrict__ src, int sh, 
 // rounds half to even (pinned against cv2 over all 65 536 (colour, pixel) pairs in
 // tests/test_oracle_post.py): (c + o) / 2 with ties to the even integer.
 // HBM-bound: reads 3*H*W (frame) + the small mask, writes 3*H*W.
-struct VizLut { uint8_t bgr[4][3]; };   // palette index 3 = "no colour" (0,0,0)
+struct VizLut { uint32_t c[4]; };   // packed b | g << 8 | r << 16 per class; index 3 = "no colour" (0)
 
 __device__ __forceinline__ int viz_class(int viz_type, int m) {
   if (viz_type == VPB_VIZ_SCENE) return (m >= 1) ? 0 : 3;                       // inRange(mask, 1, 255) -> red
@@ -113,39 +113,56 @@ __device__ __forceinline__ uint32_t blend_half_even(uint32_t c, uint32_t o) {
   return h + ((s & 1u) & (h & 1u));
 }
 
-__global__ void __launch_bounds__(256) visualize_mask_kernel(const uint8_t* __restrict__ mask, int mh, int mw,
+__global__ void __launch_bounds__(128) visualize_mask_kernel(const uint8_t* __restrict__ mask, int mh, int mw,
                                                              int viz_type, VizLut lut,
                                                              const uint8_t* __restrict__ frame, int h, int w,
                                                              int stride, uint8_t* __restrict__ out, int out_stride,
                                                              double ify, double ifx) {
-  // one thread = 4 consecutive pixels = 12 bytes = three aligned 32-bit words (when the rows allow it)
-  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
-  if (x4 >= w) return;
+  // one thread = 16 consecutive pixels = 48 bytes = three 16-byte words (when the rows allow it)
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16, y = blockIdx.y;
+  if (x0 >= w) return;
   const int sy = min(static_cast<int>(floor(y * ify)), mh - 1);
   const uint8_t* mrow = mask + static_cast<size_t>(sy) * mw;
-  const uint8_t* frow = frame + static_cast<size_t>(y) * stride + static_cast<size_t>(x4) * 3;
-  uint8_t* orow = out + static_cast<size_t>(y) * out_stride + static_cast<size_t>(x4) * 3;
-  const bool vec = (x4 + 4 <= w) && ((reinterpret_cast<uintptr_t>(frow) & 3u) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(orow) & 3u) == 0);
-  uint8_t px[12];
+  const uint8_t* frow = frame + static_cast<size_t>(y) * stride + static_cast<size_t>(x0) * 3;
+  uint8_t* orow = out + static_cast<size_t>(y) * out_stride + static_cast<size_t>(x0) * 3;
+  const bool vec = (x0 + 16 <= w) && ((reinterpret_cast<uintptr_t>(frow) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0);
   if (vec) {
-    const uint32_t* f32 = reinterpret_cast<const uint32_t*>(frow);
-    const uint32_t a = __ldg(f32), b = __ldg(f32 + 1), c = __ldg(f32 + 2);
-    *reinterpret_cast<uint32_t*>(px) = a; *reinterpret_cast<uint32_t*>(px + 4) = b; *reinterpret_cast<uint32_t*>(px + 8) = c;
-  }
-  const int npx = min(4, w - x4);
-  for (int i = 0; i < npx; ++i) {
-    const int sx = min(static_cast<int>(floor((x4 + i) * ifx)), mw - 1);
-    const int k = viz_class(viz_type, mrow[sx]);
-    for (int ch = 0; ch < 3; ++ch) {
-      const uint32_t o = vec ? px[3 * i + ch] : frow[3 * i + ch];
-      const uint8_t r = static_cast<uint8_t>(blend_half_even(lut.bgr[k][ch], o));
-      if (vec) px[3 * i + ch] = r; else orow[3 * i + ch] = r;
+    uint32_t wd[12];
+    {
+      const uint4* f4 = reinterpret_cast<const uint4*>(frow);
+      const uint4 a = __ldg(f4), b = __ldg(f4 + 1), c = __ldg(f4 + 2);
+      wd[0] = a.x; wd[1] = a.y; wd[2] = a.z; wd[3] = a.w; wd[4] = b.x; wd[5] = b.y; wd[6] = b.z; wd[7] = b.w;
+      wd[8] = c.x; wd[9] = c.y; wd[10] = c.z; wd[11] = c.w;
     }
+    uint32_t res[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) res[i] = 0;
+#pragma unroll
+    for (int px = 0; px < 16; ++px) {
+      const int sx = min(static_cast<int>(floor((x0 + px) * ifx)), mw - 1);
+      const int k = viz_class(viz_type, mrow[sx]);
+      const uint32_t cw = k == 0 ? lut.c[0] : (k == 1 ? lut.c[1] : (k == 2 ? lut.c[2] : 0u));   // selects, no local array
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const int byte = 3 * px + ch;                       // compile-time after unrolling
+        const uint32_t o = (wd[byte >> 2] >> (8 * (byte & 3))) & 0xffu;
+        res[byte >> 2] |= blend_half_even((cw >> (8 * ch)) & 0xffu, o) << (8 * (byte & 3));
+      }
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(orow);
+    o4[0] = make_uint4(res[0], res[1], res[2], res[3]);
+    o4[1] = make_uint4(res[4], res[5], res[6], res[7]);
+    o4[2] = make_uint4(res[8], res[9], res[10], res[11]);
+    return;
   }
-  if (vec) {
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(orow);
-    o32[0] = *reinterpret_cast<uint32_t*>(px); o32[1] = *reinterpret_cast<uint32_t*>(px + 4); o32[2] = *reinterpret_cast<uint32_t*>(px + 8);
+  const int npx = min(16, w - x0);
+  for (int i = 0; i < npx; ++i) {
+    const int sx = min(static_cast<int>(floor((x0 + i) * ifx)), mw - 1);
+    const int k = viz_class(viz_type, mrow[sx]);
+    const uint32_t cw = k == 0 ? lut.c[0] : (k == 1 ? lut.c[1] : (k == 2 ? lut.c[2] : 0u));
+    for (int ch = 0; ch < 3; ++ch)
+      orow[3 * i + ch] = static_cast<uint8_t>(blend_half_even((cw >> (8 * ch)) & 0xffu, frow[3 * i + ch]));
   }
 }
 
@@ -299,10 +316,11 @@ extern "C" int vpb_visualize_mask(const uint8_t* mask, int mh, int mw, int viz_t
       {{255, 93, 61}, {145, 28, 255}, {0, 0, 0}, {0, 0, 0}},          // domain: 0 orange, 255 purple
       {{255, 0, 0}, {255, 0, 200}, {0, 153, 0}, {0, 0, 0}}};          // egolanes: left, right, other
   vpb::VizLut lut;
-  memcpy(lut.bgr, kPal[viz_type], sizeof(lut.bgr));
+  for (int k = 0; k < 4; ++k)
+    lut.c[k] = kPal[viz_type][k][0] | (kPal[viz_type][k][1] << 8) | (kPal[viz_type][k][2] << 16);
   const double ifx = 1.0 / (static_cast<double>(w) / mw), ify = 1.0 / (static_cast<double>(h) / mh);
-  dim3 grid(((w + 3) / 4 + 255) / 256, h);
-  vpb::visualize_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, mh, mw, viz_type, lut, frame_bgr, h,
+  dim3 grid(((w + 15) / 16 + 127) / 128, h);
+  vpb::visualize_mask_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(mask, mh, mw, viz_type, lut, frame_bgr, h,
                                                                                  w, stride, out, out_stride, ify, ifx);
   VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
