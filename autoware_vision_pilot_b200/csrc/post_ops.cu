@@ -101,20 +101,17 @@ __global__ void resize_linear_f32_kernel(const float* __restrict__ src, int sh, 
 // rounds half to even (pinned against cv2 over all 65 536 (colour, pixel) pairs in
 // tests/test_oracle_post.py): (c + o) / 2 with ties to the even integer.
 // HBM-bound: reads 3*H*W (frame) + the small mask, writes 3*H*W.
-struct VizLut { uint32_t c[4]; };   // packed b | g << 8 | r << 16 per class; index 3 = "no colour" (0)
+// mask value -> packed colour (b | g << 8 | r << 16), one 256-entry table per visualisation type, filled by
+// the host on first use from the palettes of createColorMask
+__device__ uint32_t g_viz_tab[3][256];
 
-__device__ __forceinline__ int viz_class(int viz_type, int m) {
-  if (viz_type == VPB_VIZ_SCENE) return (m >= 1) ? 0 : 3;                       // inRange(mask, 1, 255) -> red
-  if (viz_type == VPB_VIZ_DOMAIN) return m == 0 ? 0 : (m == 255 ? 1 : 3);
-  return m <= 2 ? m : 3;                                                         // egolanes ids 0/1/2, 255 = none
-}
 __device__ __forceinline__ uint32_t blend_half_even(uint32_t c, uint32_t o) {
   const uint32_t s = c + o, h = s >> 1;
   return h + ((s & 1u) & (h & 1u));
 }
 
 __global__ void __launch_bounds__(128) visualize_mask_kernel(const uint8_t* __restrict__ mask, int mh, int mw,
-                                                             int viz_type, VizLut lut,
+                                                             int viz_type,
                                                              const uint8_t* __restrict__ frame, int h, int w,
                                                              int stride, uint8_t* __restrict__ out, int out_stride,
                                                              double ify, double ifx) {
@@ -123,6 +120,7 @@ __global__ void __launch_bounds__(128) visualize_mask_kernel(const uint8_t* __re
   if (x0 >= w) return;
   const int sy = min(static_cast<int>(floor(y * ify)), mh - 1);
   const uint8_t* mrow = mask + static_cast<size_t>(sy) * mw;
+  const uint32_t* tab = g_viz_tab[viz_type];
   const uint8_t* frow = frame + static_cast<size_t>(y) * stride + static_cast<size_t>(x0) * 3;
   uint8_t* orow = out + static_cast<size_t>(y) * out_stride + static_cast<size_t>(x0) * 3;
   const bool vec = (x0 + 16 <= w) && ((reinterpret_cast<uintptr_t>(frow) & 15u) == 0) &&
@@ -141,8 +139,7 @@ __global__ void __launch_bounds__(128) visualize_mask_kernel(const uint8_t* __re
 #pragma unroll
     for (int px = 0; px < 16; ++px) {
       const int sx = min(static_cast<int>(floor((x0 + px) * ifx)), mw - 1);
-      const int k = viz_class(viz_type, mrow[sx]);
-      const uint32_t cw = k == 0 ? lut.c[0] : (k == 1 ? lut.c[1] : (k == 2 ? lut.c[2] : 0u));   // selects, no local array
+      const uint32_t cw = tab[mrow[sx]];
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
         const int byte = 3 * px + ch;                       // compile-time after unrolling
@@ -159,8 +156,7 @@ __global__ void __launch_bounds__(128) visualize_mask_kernel(const uint8_t* __re
   const int npx = min(16, w - x0);
   for (int i = 0; i < npx; ++i) {
     const int sx = min(static_cast<int>(floor((x0 + i) * ifx)), mw - 1);
-    const int k = viz_class(viz_type, mrow[sx]);
-    const uint32_t cw = k == 0 ? lut.c[0] : (k == 1 ? lut.c[1] : (k == 2 ? lut.c[2] : 0u));
+    const uint32_t cw = tab[mrow[sx]];
     for (int ch = 0; ch < 3; ++ch)
       orow[3 * i + ch] = static_cast<uint8_t>(blend_half_even((cw >> (8 * ch)) & 0xffu, frow[3 * i + ch]));
   }
@@ -310,17 +306,24 @@ extern "C" int vpb_visualize_mask(const uint8_t* mask, int mh, int mw, int viz_t
     vpb_set_error("visualize_mask: bad arguments");
     return VPB_ERR_ARG;
   }
-  // palettes of createColorMask (masks_visualization_engine.cpp:40-60), BGR
-  static const uint8_t kPal[3][4][3] = {
-      {{0, 0, 255}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}},                 // scene: foreground red
-      {{255, 93, 61}, {145, 28, 255}, {0, 0, 0}, {0, 0, 0}},          // domain: 0 orange, 255 purple
-      {{255, 0, 0}, {255, 0, 200}, {0, 153, 0}, {0, 0, 0}}};          // egolanes: left, right, other
-  vpb::VizLut lut;
-  for (int k = 0; k < 4; ++k)
-    lut.c[k] = kPal[viz_type][k][0] | (kPal[viz_type][k][1] << 8) | (kPal[viz_type][k][2] << 16);
+  // createColorMask (masks_visualization_engine.cpp:40-60) as a value -> BGR table, uploaded once per device
+  static bool tab_ready[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !tab_ready[dev]) {
+    static uint32_t tab[3][256];
+    auto bgr = [](int b, int g, int r) { return static_cast<uint32_t>(b | (g << 8) | (r << 16)); };
+    for (int m = 0; m < 256; ++m) {
+      tab[VPB_VIZ_SCENE][m] = m >= 1 ? bgr(0, 0, 255) : 0u;                                  // inRange(mask, 1, 255) -> red
+      tab[VPB_VIZ_DOMAIN][m] = m == 0 ? bgr(255, 93, 61) : (m == 255 ? bgr(145, 28, 255) : 0u);
+      tab[VPB_VIZ_EGOLANES][m] = m == 0 ? bgr(255, 0, 0) : (m == 1 ? bgr(255, 0, 200) : (m == 2 ? bgr(0, 153, 0) : 0u));
+    }
+    VPB_CUDA_OK(cudaMemcpyToSymbol(vpb::g_viz_tab, tab, sizeof(tab)));
+    tab_ready[dev] = true;
+  }
   const double ifx = 1.0 / (static_cast<double>(w) / mw), ify = 1.0 / (static_cast<double>(h) / mh);
   dim3 grid(((w + 15) / 16 + 127) / 128, h);
-  vpb::visualize_mask_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(mask, mh, mw, viz_type, lut, frame_bgr, h,
+  vpb::visualize_mask_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(mask, mh, mw, viz_type, frame_bgr, h,
                                                                                  w, stride, out, out_stride, ify, ifx);
   VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
