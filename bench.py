@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-stream", action="store_true", help="disable the concurrent per-model lanes")
-    ap.add_argument("--inflight", type=int, default=2,
+    ap.add_argument("--inflight", type=int, default=3,
                     help="camera frames in flight per GPU (engine replicas on separate streams; the next "
                          "frame's latency-bound encoder overlaps the current frame's decoders)")
     args = ap.parse_args()
