@@ -200,12 +200,54 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
   }
 }
 
+// Lean form of the above for the two dominant cases — plain store with no activation (ConvTranspose + skip,
+// 1x1 projections) or GELU (every 3x3 of context / neck / heads) — when the whole N tile lies inside the
+// output row (no per-store predicates).  The epilogue is latency-bound on its instruction chain (ncu: ~16
+// cycles per issued instruction, 77 instructions per chunk in the generic form, most of them uniform
+// mode/activation tests and address arithmetic): here pointers advance by constants and nothing is tested
+// inside the loop.
+template <class E, bool GELU>
+__device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32_t t_row, int n0,
+                                                    const float* sbias, int part, const EpiPix& px) {
+  const int nchunks = p.BN >> 4;
+  typename E::T* op = reinterpret_cast<typename E::T*>(p.out) + (px.ooff + n0 + part * 16);
+  const float4* sb4 = reinterpret_cast<const float4*>(sbias + part * 16);
+  uint32_t ta = t_row + part * 16;
+  const bool ok = px.ok, zero = px.zero;
+  for (int chunk = part; chunk < nchunks; chunk += 4, op += 64, sb4 += 16, ta += 64) {
+    uint32_t rr[16];
+    tmem_ld16(ta, rr);                     // .sync.aligned: every lane takes part, stores are predicated
+    tmem_ld_wait();
+    float2 v[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = sb4[i];
+      v[2 * i] = fadd2(make_float2(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1])), make_float2(b4.x, b4.y));
+      v[2 * i + 1] = fadd2(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(b4.z, b4.w));
+    }
+    if (GELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = act_gelu2(v[i]);
+    }
+    uint4 o0, o1;
+    o0.x = pack2<E>(v[0].x, v[0].y); o0.y = pack2<E>(v[1].x, v[1].y); o0.z = pack2<E>(v[2].x, v[2].y); o0.w = pack2<E>(v[3].x, v[3].y);
+    o1.x = pack2<E>(v[4].x, v[4].y); o1.y = pack2<E>(v[5].x, v[5].y); o1.z = pack2<E>(v[6].x, v[6].y); o1.w = pack2<E>(v[7].x, v[7].y);
+    if (zero) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }
+    if (ok || zero) {
+      reinterpret_cast<uint4*>(op)[0] = o0;
+      reinterpret_cast<uint4*>(op)[1] = o1;
+    }
+  }
+}
+
 template <class E>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_row, int n0,
                                               const float* sbias, int part, const EpiPix& px) {
   // NC = 2 (two chunks per iteration) measured 2-3 % slower and makes ptxas spill in every kernel that
   // contains it (96-register cap), so only the one-chunk form is instantiated.
-  epilogue_chunks<E, 1>(p, t_row, n0, sbias, part, px);
+  if (p.mode == VPB_EPI_STORE && n0 + p.BN <= p.ldo && p.act == ACT_GELU) epilogue_store_fast<E, true>(p, t_row, n0, sbias, part, px);
+  else if (p.mode == VPB_EPI_STORE && n0 + p.BN <= p.ldo && p.act == ACT_NONE) epilogue_store_fast<E, false>(p, t_row, n0, sbias, part, px);
+  else epilogue_chunks<E, 1>(p, t_row, n0, sbias, part, px);
 }
 
 __device__ __forceinline__ void stage_bias(const ConvKParams& p, float* dst, int etid, int n0) {
