@@ -311,6 +311,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
   const uint32_t tmem_base = tmem_holder;
   pdl_launch_dependents();   // let the next kernel's prologue overlap this kernel
   pdl_wait();                // predecessor's outputs (our inputs) are complete and visible from here on
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[255] = clock64();
 
   const int kiters = p.taps * p.kchunks;
   const int kiters_all = kiters + p.kchunks2;   // + the fused skip link's K chunks
@@ -340,6 +341,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
           if (elect_one()) {
             const uint32_t full = smem_u32(&bar_full[stage]);
             const uint32_t sa = smem_base + stage * stage_bytes;
+            if (p.trace && blockIdx.x == 0) {
+              const int ti = (tile - blockIdx.x) / gridDim.x, k = t * p.kchunks + c;
+              if (ti < 16 && k < 4) p.trace[ti * 16 + k] = clock64();
+            }
             mbar_arrive_expect_tx(full, stage_bytes);
             tma_load_4d(sa, &mapA, full, c * 64, w0 + dx, h0 + dy, 0);
             if (p.fuse4) {
@@ -382,6 +387,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
       const uint32_t aphase = p.fuse4 ? (it & 1) : ((it >> 1) & 1);
       mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
       tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && it < 16 && lane == 0) p.trace[it * 16 + 9] = clock64();
       const uint32_t d_tmem = tmem_base + as * kAccStride;
       for (int k = 0; k < kiters_all; ++k) {
         const int c = k % p.kchunks;
@@ -390,6 +396,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
         if (elect_one()) {
+          if (p.trace && blockIdx.x == 0 && it < 16) {
+            if (k < 4) p.trace[it * 16 + 4 + k] = clock64();
+            if (k == kiters_all - 1) p.trace[it * 16 + 8] = clock64();
+          }
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint64_t adesc = umma_desc_k128(sa);
           for (int q4 = 0; q4 < nb_tiles; ++q4) {
@@ -434,8 +444,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
       const int h = thi * p.TH + lh, w = twi * p.TW + lw, n0 = nt * p.BN;
 
       stage_bias(p, s_bias[as], etid, n0);
+      if (p.trace && blockIdx.x == 0 && it < 16 && etid == 0) p.trace[it * 16 + 10] = clock64();
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && it < 16 && etid == 0) p.trace[it * 16 + 11] = clock64();
       for (int q4 = 0; q4 < nb_tiles; ++q4) {
         const int ph = ph0 + q4;
         const int oh = (p.phases > 1) ? 2 * h + (ph >> 1) : h;
@@ -451,6 +463,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
       }
       tc_fence_before();
       __syncwarp();
+      if (p.trace && blockIdx.x == 0 && it < 16 && etid == 0) p.trace[it * 16 + 12] = clock64();
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
     }
   }
@@ -1093,6 +1106,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.act = a->act; p.mode = a->mode; p.final_kind = a->final_kind;
   p.bias = a->bias; p.out = a->out; p.ldo = a->ldo; p.res = a->res; p.ldr = a->ldr;
   p.out_f32 = a->out_f32; p.out_cls = a->out_cls;
+  p.trace = a->dbg_trace;
   plan->dtype = a->dtype;
   plan->grid = p.pair ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
                       : std::min(p.total_tiles, device_sm_count());

@@ -36,6 +36,7 @@ struct ConvKParams {
   int ldr;
   float* out_f32;
   uint8_t* out_cls;
+  unsigned long long* trace;     // experiment hook (tile kernel): clock64() stamps of CTA 0, [16 tiles][16]
 };
 
 struct ConvPlan {
