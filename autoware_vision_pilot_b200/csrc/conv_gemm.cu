@@ -214,14 +214,11 @@ __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32
   const float4* sb4 = reinterpret_cast<const float4*>(sbias + part * 16);
   uint32_t ta = t_row + part * 16;
   const bool ok = px.ok, zero = px.zero;
-  for (int chunk = part; chunk < nchunks; chunk += 4, op += 64, sb4 += 16, ta += 64) {
-    uint32_t rr[16];
-    tmem_ld16(ta, rr);                     // .sync.aligned: every lane takes part, stores are predicated
-    tmem_ld_wait();
+  auto finish = [&](const uint32_t (&rr)[16], const float4* sb, typename E::T* o) {
     float2 v[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b4 = sb4[i];
+      const float4 b4 = sb[i];
       v[2 * i] = fadd2(make_float2(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1])), make_float2(b4.x, b4.y));
       v[2 * i + 1] = fadd2(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(b4.z, b4.w));
     }
@@ -234,9 +231,26 @@ __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32
     o1.x = pack2<E>(v[4].x, v[4].y); o1.y = pack2<E>(v[5].x, v[5].y); o1.z = pack2<E>(v[6].x, v[6].y); o1.w = pack2<E>(v[7].x, v[7].y);
     if (zero) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }
     if (ok || zero) {
-      reinterpret_cast<uint4*>(op)[0] = o0;
-      reinterpret_cast<uint4*>(op)[1] = o1;
+      reinterpret_cast<uint4*>(o)[0] = o0;
+      reinterpret_cast<uint4*>(o)[1] = o1;
     }
+  };
+  int chunk = part;
+  // two chunks per TMEM wait while at least two remain (the drain is bound by TMEM read latency / bandwidth,
+  // profiles/r1_convt_timeline.md), then the odd one
+  for (; chunk + 4 < nchunks; chunk += 8, op += 128, sb4 += 32, ta += 128) {
+    uint32_t ra[16], rb[16];
+    tmem_ld16(ta, ra);                     // .sync.aligned: every lane takes part, stores are predicated
+    tmem_ld16(ta + 64, rb);
+    tmem_ld_wait();
+    finish(ra, sb4, op);
+    finish(rb, sb4 + 16, op + 64);
+  }
+  if (chunk < nchunks) {
+    uint32_t ra[16];
+    tmem_ld16(ta, ra);
+    tmem_ld_wait();
+    finish(ra, sb4, op);
   }
 }
 
