@@ -869,6 +869,32 @@ extern "C" int vp_engine_profile(vp_engine* e, int max_ops, float* ms, double* f
   return VPB_OK;
 }
 
+extern "C" int vp_engine_time_kind(vp_engine* e, int kind, int reps, float* ms, double* flops, int* launches) {
+  if (!e || !ms || reps <= 0) return VPB_ERR_ARG;
+  if (!e->g_src) { vpb_set_error("vp_engine_time_kind: run one inference first"); return VPB_ERR_STATE; }
+  cudaEvent_t a, b;
+  VPB_CUDA_OK(cudaEventCreate(&a));
+  VPB_CUDA_OK(cudaEventCreate(&b));
+  double fl = 0.0;
+  int n = 0;
+  for (int r = -1; r < reps; ++r) {            // r = -1: untimed warm-up pass
+    if (r == 0) VPB_CUDA_OK(cudaEventRecord(a, e->stream));
+    for (auto& op : e->ops) {
+      if (!op.gemm || op.kind != kind) continue;
+      const int rc = op.launch(e->stream);
+      if (rc) return rc;
+      if (r >= 0) { fl += op.flops; ++n; }
+    }
+  }
+  VPB_CUDA_OK(cudaEventRecord(b, e->stream));
+  VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
+  VPB_CUDA_OK(cudaEventElapsedTime(ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  if (flops) *flops = fl;
+  if (launches) *launches = n;
+  return VPB_OK;
+}
+
 extern "C" int vp_engine_read_resized(vp_engine* e, uint8_t* dst) {
   if (!e || !dst) return VPB_ERR_ARG;
   VPB_CUDA_OK(cudaMemcpyAsync(dst, e->d_resized, static_cast<size_t>(kNetH) * kNetW * 3, cudaMemcpyDeviceToHost, e->stream));

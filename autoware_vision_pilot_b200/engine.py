@@ -164,6 +164,15 @@ class Engine:
         return [{"name": names[i].decode(), "ms": ms[i], "flops": fl[i], "gemm": bool(gemm[i]),
                  "kernel": kern.get(gemm[i])} for i in range(cnt.value)]
 
+    def time_kernel(self, kind: int, reps: int = 10) -> dict:
+        """Back-to-back device time of every launch of one convolution kernel (1 tile, 2 lin, 3 pair)."""
+        ms, fl, n = C.c_float(), C.c_double(), C.c_int()
+        self._lib.vp_engine_time_kind.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                                  C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.check(self._lib.vp_engine_time_kind(self._h, kind, reps, C.byref(ms), C.byref(fl), C.byref(n)),
+                "vp_engine_time_kind")
+        return {"ms": ms.value, "flops": fl.value, "launches": n.value}
+
     def read_resized(self) -> np.ndarray:
         buf = np.empty((320, 640, 3), dtype=np.uint8)
         L.check(self._lib.vp_engine_read_resized(self._h, buf.ctypes.data), "vp_engine_read_resized")

@@ -114,6 +114,12 @@ int vp_engine_get_stats(const vp_engine* e, vp_engine_stats* s);
  * names[i] point into engine-owned storage. */
 int vp_engine_profile(vp_engine* e, int max_ops, float* ms, double* flops, const char** names,
                       int* is_gemm, int* n_ops);
+/* Device time of all launches of ONE convolution kernel (kind as in is_gemm above) of the frame, issued
+ * back to back `reps` times between a single CUDA-event pair on the engine's stream (after one untimed
+ * pass): ms = total, flops = algorithmic 2*MAC of the timed launches.  This is the "average launch
+ * duration of the dominant kernel" bench.py's roofline uses; the operands of the ~30 layers cycle through
+ * more memory than L2 holds. */
+int vp_engine_time_kind(vp_engine* e, int kind, int reps, float* ms, double* flops, int* launches);
 /* Intermediate activations for the per-tap parity tests: copies tensor `name`
  * ("<model_idx>/f0".."f4", "context", "neck", "pre") to host as fp32 NCHW. Returns element count. */
 long vp_engine_read_tap(vp_engine* e, const char* name, float* dst, long cap, int* c, int* h, int* w);
