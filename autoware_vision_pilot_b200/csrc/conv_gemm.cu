@@ -6,7 +6,7 @@
 //   nn.Conv2d 1x1         scene_neck.py:12,17,22 (skip links) and EfficientNet-B0 pointwise convs
 //   nn.ConvTranspose2d k2 s2   scene_neck.py:11,16,21, scene_seg_head.py:11,16
 //
-// Two main loops share one epilogue.
+// Three main loops share one epilogue.
 //
 // (1) conv_gemm_kernel — "tile" formulation, any of the three op types.
 //     Activations are NHWC 16-bit.  For an output tile of 128 pixels (a TH x TW patch) and BN
@@ -14,6 +14,9 @@
 //     with M = 128, N = BN, K = taps*Cin.  The A operand for one (tap, 64-channel chunk) is one 4-D
 //     TMA box {64 ch, TW, TH, 1} at the shifted coordinate; out-of-range rows/columns are
 //     zero-filled by the TMA unit, which IS the convolution's zero padding.
+//     ConvTranspose = 4 phase GEMMs (output pixel (2h+a, 2w+b)); the neck's skip link
+//     ConvT(in) + Conv1x1(skip) is ONE GEMM: the skip tensor is a second K segment read at output
+//     resolution through a 5-D TMA view [h][a][w][b][c] into the same accumulator.
 //
 // (2) conv3x3_lin_kernel — "linear padded" formulation for the 3x3 layers that carry > 90 % of the
 //     FLOPs.  Input and output live in HBM as zero-bordered images [(H+2)*(W+2)][C]; the GEMM M
@@ -25,9 +28,14 @@
 //     field must stay 0 for these row-shifted views (setting it to dx gives wrong results).
 //     A traffic from L2 drops 9 -> 3.05 loads per chunk and TMA issue count halves; B (weights)
 //     stream through their own ring.  Border pixels are written as zeros, so the output is again
-//     a valid zero-bordered image for the next layer.
+//     a valid zero-bordered image for the next layer.  Used for 3x3 layers with < 96 tiles.
 //
-// Both: operands land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma reads
+// (3) conv3x3_pair_kernel — formulation (2) on a CTA pair (cluster of 2, tcgen05.mma.cta_group::2,
+//     M = 256): each CTA stages its own pixels and HALF of every weight tile.  The dominant kernel
+//     (every 3x3 layer with >= 96 tiles); see the comment above the kernel and
+//     profiles/r1_smem_operand_model.md for why halving the weight operand per SM is what counts.
+//
+// All: operands land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma reads
 // through descriptors; fp32 accumulators in TMEM, two of them, so the epilogue of tile i overlaps
 // the main loop of tile i+1; persistent grid; warp-specialised:
 //   warp 0       TMA producer (one elected lane)
@@ -39,6 +47,7 @@
 //                stage, hence 16 warps, a branch-free GELU and no per-element global loads.
 #include "common.cuh"
 #include "conv_gemm.cuh"
+#include "ops_internal.h"
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
@@ -929,13 +938,10 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int device_sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
 }
 
 static int pick_bn(int Cout) {
@@ -1209,15 +1215,18 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
 }
 
 int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    VPB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    VPB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_lin_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_lin_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attr_set = true;
+  {
+    std::lock_guard<std::mutex> g(init_mutex());
+    bool* done = device_flag(kInitConv);
+    if (!*done) {
+      VPB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_lin_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_lin_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      *done = true;
+    }
   }
   const bool bf = plan->dtype == VPB_BF16;
   const dim3 g(plan->grid), b(kThreads);

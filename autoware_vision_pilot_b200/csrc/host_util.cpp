@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include "../../include/vp_b200_ops.h"
+#include "ops_internal.h"
 
 static thread_local char g_err[1024] = "";
 
@@ -13,3 +14,17 @@ extern "C" void vpb_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+namespace vpb {
+std::mutex& init_mutex() {
+  static std::mutex m;
+  return m;
+}
+bool* device_flag(InitSlot slot) {
+  static bool flags[kInitSlots][64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 63;
+  return &flags[slot][dev];
+}
+}  // namespace vpb

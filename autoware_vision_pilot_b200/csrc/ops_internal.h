@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <vector>
+#include <mutex>
 #include "../../include/vp_b200_ops.h"
 
 namespace vpb {
@@ -36,5 +37,12 @@ struct DwGeom {
   int Ho, Wo, G, PPB, threads, pix_per_block, nblocks;
 };
 DwGeom dw_geometry(int H, int W, int C, int k, int stride);
+
+// One-time per-DEVICE initialisation (function attributes, constant tables): engines for several GPUs may
+// live in one process, and entry points may be called from several threads.
+//   { std::lock_guard<std::mutex> g(init_mutex()); bool* done = device_flag(kInitConv); if (!*done) { ...; *done = true; } }
+enum InitSlot { kInitConv = 0, kInitPreprocess = 1, kInitVizTable = 2, kInitSlots = 4 };
+std::mutex& init_mutex();
+bool* device_flag(InitSlot slot);    // flag of `slot` for the calling thread's current CUDA device
 
 }  // namespace vpb

@@ -307,19 +307,20 @@ extern "C" int vpb_visualize_mask(const uint8_t* mask, int mh, int mw, int viz_t
     return VPB_ERR_ARG;
   }
   // createColorMask (masks_visualization_engine.cpp:40-60) as a value -> BGR table, uploaded once per device
-  static bool tab_ready[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !tab_ready[dev]) {
-    static uint32_t tab[3][256];
-    auto bgr = [](int b, int g, int r) { return static_cast<uint32_t>(b | (g << 8) | (r << 16)); };
-    for (int m = 0; m < 256; ++m) {
-      tab[VPB_VIZ_SCENE][m] = m >= 1 ? bgr(0, 0, 255) : 0u;                                  // inRange(mask, 1, 255) -> red
-      tab[VPB_VIZ_DOMAIN][m] = m == 0 ? bgr(255, 93, 61) : (m == 255 ? bgr(145, 28, 255) : 0u);
-      tab[VPB_VIZ_EGOLANES][m] = m == 0 ? bgr(255, 0, 0) : (m == 1 ? bgr(255, 0, 200) : (m == 2 ? bgr(0, 153, 0) : 0u));
+  {
+    std::lock_guard<std::mutex> g(vpb::init_mutex());
+    bool* done = vpb::device_flag(vpb::kInitVizTable);
+    if (!*done) {
+      static uint32_t tab[3][256];
+      auto bgr = [](int b, int g2, int r) { return static_cast<uint32_t>(b | (g2 << 8) | (r << 16)); };
+      for (int m = 0; m < 256; ++m) {
+        tab[VPB_VIZ_SCENE][m] = m >= 1 ? bgr(0, 0, 255) : 0u;                                  // inRange(mask, 1, 255) -> red
+        tab[VPB_VIZ_DOMAIN][m] = m == 0 ? bgr(255, 93, 61) : (m == 255 ? bgr(145, 28, 255) : 0u);
+        tab[VPB_VIZ_EGOLANES][m] = m == 0 ? bgr(255, 0, 0) : (m == 1 ? bgr(255, 0, 200) : (m == 2 ? bgr(0, 153, 0) : 0u));
+      }
+      VPB_CUDA_OK(cudaMemcpyToSymbol(vpb::g_viz_tab, tab, sizeof(tab)));
+      *done = true;
     }
-    VPB_CUDA_OK(cudaMemcpyToSymbol(vpb::g_viz_tab, tab, sizeof(tab)));
-    tab_ready[dev] = true;
   }
   const double ifx = 1.0 / (static_cast<double>(w) / mw), ify = 1.0 / (static_cast<double>(h) / mh);
   dim3 grid(((w + 15) / 16 + 127) / 128, h);

@@ -355,11 +355,14 @@ int PreprocessPlan::launch(const uint8_t* src, int stride, int convention, int d
   fill_params(*this, src, stride, convention, out, out_u8, p);
   if (mode == VPB_RESIZE_PIL_BICUBIC) {
     dim3 grid((OW + kTX - 1) / kTX, (OH + kTY - 1) / kTY);
-    static bool attr_done = false;
-    if (!attr_done) {
-      VPB_CUDA_OK(cudaFuncSetAttribute(preprocess_pil_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      VPB_CUDA_OK(cudaFuncSetAttribute(preprocess_pil_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done = true;
+    {
+      std::lock_guard<std::mutex> g(init_mutex());
+      bool* done = device_flag(kInitPreprocess);
+      if (!*done) {
+        VPB_CUDA_OK(cudaFuncSetAttribute(preprocess_pil_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VPB_CUDA_OK(cudaFuncSetAttribute(preprocess_pil_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        *done = true;
+      }
     }
     if (dtype == VPB_BF16) VPB_CUDA_OK(launch_k(preprocess_pil_kernel<BF16>, grid, dim3(256), smem_bytes, stream, p, rows_cap, patch_w_cap));
     else VPB_CUDA_OK(launch_k(preprocess_pil_kernel<F16>, grid, dim3(256), smem_bytes, stream, p, rows_cap, patch_w_cap));
