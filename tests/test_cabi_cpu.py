@@ -106,3 +106,35 @@ def test_engine_create_fails_loudly_without_gpu(tmp_path):
     from autoware_vision_pilot_b200 import engine as E
     with pytest.raises(RuntimeError):
         E.Engine([E.SCENE_SEG], [str(tmp_path / "missing.vpw")])
+
+
+def test_ctypes_mirrors_match_the_c_struct_layouts(tmp_path):
+    """The headers are the contract; the ctypes Structures in _lib.py / engine.py are hand-written mirrors.
+    A C program compiled against include/*.h prints sizeof / offsetof of every struct and field, which must
+    equal what ctypes computes — catches a field added on one side only."""
+    import subprocess
+    from autoware_vision_pilot_b200 import engine as E
+    mirrors = {
+        "vpb_conv_args": (L.ConvArgs, {"inp": "in"}),
+        "vpb_lateral_state": (L.LateralState, {}),
+        "vpb_lateral_out": (L.LateralOut, {}),
+        "vp_engine_config": (E._Config, {}),
+        "vp_output": (E._Output, {}),
+        "vp_engine_stats": (E._Stats, {}),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vp_b200.h"', '#include "vp_b200_ops.h"',
+             'int main(void) {']
+    for cname, (cls, rename) in mirrors.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {rename.get(fname, fname)}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, (cls, _) in mirrors.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
