@@ -36,7 +36,7 @@ class ConvArgs(C.Structure):
         ("algo", C.c_int), ("dbg_ms", C.c_int), ("dbg_gb", C.c_int), ("dbg_base_offset", C.c_int),
         ("in2", C.c_void_p), ("w2", C.c_void_p),
         ("Cin2", C.c_int), ("ld2", C.c_int), ("in2_pad", C.c_int), ("dbg_pair", C.c_int),
-        ("dbg_trace", C.c_void_p),
+        ("dbg_splitk", C.c_int), ("dbg_trace", C.c_void_p),
     ]
 
 

@@ -330,6 +330,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       : "memory");
 }
 
+// 16-byte load from the shared memory of CTA `cta` of the cluster, same offset as local address `addr`
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr, uint32_t cta) {
+  float4 v;
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %4, %5;\n\t"
+      "ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [ra];\n\t}"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "r"(addr), "r"(cta)
+      : "memory");
+  return v;
+}
+
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 // rows are 128 B apart inside an 8-row (1024 B) swizzle atom, atoms are SBO apart.
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4
@@ -396,6 +409,20 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// Same, with a runtime cluster size along x (kernels without __cluster_dims__).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 }  // namespace vpb

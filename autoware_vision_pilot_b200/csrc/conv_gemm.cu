@@ -917,6 +917,214 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// (4) linear padded formulation with the K loop split over a cluster (small-M layers)
+//
+// The 10x20 / 20x40 layers (context, first neck block) have 3-8 M tiles but 36-180 (chunk, kernel-row)
+// groups in their K loop: with one CTA per output tile at most 48-96 SMs work and each walks a long
+// latency-bound K loop.  Here a cluster of S = 2..4 CTAs shares ONE output tile (128 pixels x BN):
+// CTA r accumulates K chunks [r*kc/S, (r+1)*kc/S) into its own TMEM accumulator, writes the fp32 partial
+// to its shared memory, and after a cluster barrier CTA r sums the S partials of ITS 128/S rows through
+// distributed shared memory in rank order (deterministic) and runs the epilogue (bias, activation,
+// residual, zero border).  One tile per CTA (not persistent), ms = 1, gb = 3, BN <= 128.
+// ------------------------------------------------------------------------------------------------
+template <class E>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_splitk_kernel(const __grid_constant__ CUtensorMap mapA,
+                      const __grid_constant__ CUtensorMap mapB, const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kMaxRing], a_empty[kMaxRing];
+  __shared__ __align__(8) uint64_t b_full[kMaxRing], b_empty[kMaxRing];
+  __shared__ __align__(8) uint64_t bar_tfull;
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_bias[256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.splitk;
+  const uint32_t rank = cluster_ctarank();
+  const int tile = blockIdx.x / S;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t seg_bytes = seg_slot_bytes(1);
+  const uint32_t b_base = smem_base + p.na * seg_bytes;
+  const int mt = static_cast<int>(fast_div(tile, p.mg_tn)), nt = tile - mt * p.tiles_n;
+  const int p0 = mt * 128, n0 = nt * p.BN;
+  const int c_beg = static_cast<int>(rank) * p.kchunks / S, c_end = (static_cast<int>(rank) + 1) * p.kchunks / S;
+  const int pstride = p.BN + 4;                       // floats per row of the partial buffer (bank spreading)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.na; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
+    mbar_init(smem_u32(&bar_tfull), 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tmem_holder), 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int c = c_beg; c < c_end; ++c) {
+      for (int dy = 0; dy < 3; ++dy) {
+        mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1u);
+        if (elect_one()) {
+          const uint32_t af = smem_u32(&a_full[sa]);
+          mbar_arrive_expect_tx(af, kSegRows * 128);
+          tma_load_2d(smem_base + sa * seg_bytes, &mapA, af, c * 64, p0 + (dy - 1) * p.WP - 1);
+        }
+        __syncwarp();
+        if (++sa == p.na) { sa = 0; pa ^= 1u; }
+        mbar_wait(smem_u32(&b_empty[sb]), pb ^ 1u);
+        if (elect_one()) {
+          const uint32_t bf = smem_u32(&b_full[sb]);
+          mbar_arrive_expect_tx(bf, 3 * b_bytes);
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+            tma_load_3d(b_base + (sb * 3 + dx) * b_bytes, &mapB, bf, c * 64, n0, dy * 3 + dx);
+        }
+        __syncwarp();
+        if (++sb == p.nb) { sb = 0; pb ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc(E::kUmmaFmt, 128, p.BN);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    uint32_t first = 1;
+    for (int c = c_beg; c < c_end; ++c) {
+      const int kvalid = min(64, p.Cin - c * 64);
+      const int ksteps = (kvalid + 15) >> 4;
+      for (int dy = 0; dy < 3; ++dy) {
+        const bool last = (c == c_end - 1) && (dy == 2);
+        mbar_wait(smem_u32(&a_full[sa]), pa);
+        mbar_wait(smem_u32(&b_full[sb]), pb);
+        tc_fence_after();
+        const uint32_t seg = smem_base + sa * seg_bytes;
+        if (elect_one()) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint64_t adesc = umma_desc_k128(seg + dx * 128);
+            const uint64_t bdesc = umma_desc_k128(b_base + (sb * 3 + dx) * b_bytes);
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_f16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+            first = 0;
+          }
+          umma_commit(smem_u32(&b_empty[sb]));
+          umma_commit(smem_u32(&a_empty[sa]));
+          if (last) umma_commit(smem_u32(&bar_tfull));
+        }
+        __syncwarp();
+        first = 0;
+        if (++sb == p.nb) { sb = 0; pb ^= 1u; }
+        if (++sa == p.na) { sa = 0; pa ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ accumulator -> fp32 partial in shared memory
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    const int row = q * 32 + lane;
+    stage_bias(p, s_bias, etid, n0);
+    if (c_end > c_beg) mbar_wait(smem_u32(&bar_tfull), 0);   // every MMA of this CTA has retired: the ring may be overwritten
+    tc_fence_after();
+    float* part_buf = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int nchunks = p.BN >> 4;
+    for (int chunk = part; chunk < nchunks; chunk += 4) {
+      uint32_t rr[16];
+      tmem_ld16(t_row + chunk * 16, rr);
+      tmem_ld_wait();
+      if (c_end <= c_beg) {                 // no K chunk for this rank (S > kchunks): contributes zeros
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rr[i] = 0u;
+      }
+      float4* dst = reinterpret_cast<float4*>(part_buf + row * pstride + chunk * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dst[i] = make_float4(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1]), __uint_as_float(rr[4 * i + 2]),
+                             __uint_as_float(rr[4 * i + 3]));
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  cluster_sync_all();                         // all S partials are in shared memory and visible cluster-wide
+
+  if (warp >= 2) {
+    // ------------------------------------------------------------ reduce my rows over the cluster + epilogue
+    const int etid = threadIdx.x - 64;
+    const int rows_per = (128 + S - 1) / S;
+    const int r_beg = static_cast<int>(rank) * rows_per, r_end = min(128, r_beg + rows_per);
+    const int c4n = p.BN >> 2;                                      // float4 groups per row
+    const uint32_t part_addr = smem_base;
+    typename E::T* out = reinterpret_cast<typename E::T*>(p.out);
+    const typename E::T* res = reinterpret_cast<const typename E::T*>(p.res);
+    for (int item = etid; item < (r_end - r_beg) * c4n; item += kEpiWarps * 32) {
+      const int rl = item / c4n, c4 = item - rl * c4n;
+      const int row = r_beg + rl;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t addr = part_addr + static_cast<uint32_t>(row * pstride + c4 * 4) * 4u;
+      for (int s = 0; s < S; ++s) {                                 // fixed order: deterministic
+        const float4 v = ld_dsmem_f4(addr, static_cast<uint32_t>(s));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const int pp = p0 + row;
+      if (pp >= p.NP) continue;
+      const int y = static_cast<int>(fast_div(pp, p.mg_wp)), x = pp - y * p.WP;
+      const bool inside = y >= 1 && y <= p.H && x >= 1 && x <= p.W;
+      const int n = n0 + c4 * 4;
+      if (n >= p.ldo) continue;
+      const uint32_t upix = static_cast<uint32_t>((y - 1) * p.W + (x - 1));
+      typename E::T* op = out + ((p.out_pad ? static_cast<uint32_t>(pp) : upix) * p.ldo + n);
+      if (!inside) {
+        if (p.out_pad) *reinterpret_cast<uint2*>(op) = make_uint2(0u, 0u);
+        continue;
+      }
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c4 * 4);
+      float v[4] = {acc.x + b4.x, acc.y + b4.y, acc.z + b4.z, acc.w + b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (p.act == ACT_GELU) v[i] = act_gelu(v[i]);
+        else if (p.act == ACT_SILU) v[i] = act_silu(v[i]);
+        else if (p.act == ACT_SIGMOID) v[i] = (n + i < p.Cout) ? act_sigmoid(v[i]) : 0.f;
+      }
+      if ((p.mode == VPB_EPI_ADD || p.mode == VPB_EPI_MULADD) && n < p.ldr) {
+        const typename E::T* rp = res + ((p.res_pad ? static_cast<uint32_t>(pp) : upix) * p.ldr + n);
+        const uint2 rv = *reinterpret_cast<const uint2*>(rp);
+        const float2 f0 = unpack2<E>(rv.x), f1 = unpack2<E>(rv.y);
+        const float f[4] = {f0.x, f0.y, f1.x, f1.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (p.mode == VPB_EPI_ADD) ? v[i] + f[i] : fmaf(v[i], f[i], f[i]);
+      }
+      *reinterpret_cast<uint2*>(op) = make_uint2(pack2<E>(v[0], v[1]), pack2<E>(v[2], v[3]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                         // peers may still be reading this CTA's partial
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1013,6 +1221,26 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
+  // split-K over a cluster for the small-M layers: at most half of the SMs would get a tile at BN = 128
+  p.splitk = 0;
+  if (lin && a->mode != VPB_EPI_FINAL && a->dbg_splitk >= 0 && (a->bn <= 0 || a->dbg_splitk >= 2)) {
+    int bn = 128;
+    if (a->Cout < 128) bn = (a->Cout + 15) / 16 * 16;
+    else {
+      int best_waste = 1 << 30;
+      for (int b = 128; b >= 64; b -= 16) {
+        const int waste = (a->Cout + b - 1) / b * b - a->Cout;
+        if (waste < best_waste) { best_waste = waste; bn = b; }
+      }
+    }
+    if (a->bn > 0) bn = std::min(a->bn, 128);
+    const int tiles = ((p.NP + 127) / 128) * ((a->Cout + bn - 1) / bn);
+    const int kc = (a->Cin + 63) / 64;
+    int S = 0;
+    if (a->dbg_splitk >= 2) S = std::min(std::min(a->dbg_splitk, 8), kc);
+    else if (a->Cout >= 128 && 2 * tiles <= device_sm_count()) S = std::min(std::min(4, device_sm_count() / tiles), kc / 2);
+    if (S >= 2) { p.splitk = S; p.BN = bn; }
+  }
   bool convt_fused_bn = false;
   if (a->bn <= 0 && a->phases == 4 && p.BN > 128) {
     // ConvTranspose: the fused form (all four phases per tile, 4 accumulators) needs an N tile <= 128;
@@ -1032,7 +1260,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     if (a->dbg_ms == 2 || (a->dbg_ms != 1 && !a->in2 && sp * ((a->Cout + best - 1) / best) >= 2 * device_sm_count()))
       { p.BN = best; convt_fused_bn = true; }
   }
-  if (!convt_fused_bn && a->bn <= 0 && a->Cout >= 128) {
+  if (!convt_fused_bn && !p.splitk && a->bn <= 0 && a->Cout >= 128) {
     // small-M layers (context, first neck blocks): trade N-tile width for CTA count so that the
     // persistent grid covers more of the 148 SMs (weights are re-streamed from L2, activations
     // are tiny)
@@ -1054,7 +1282,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.Cin2 = a->in2 ? a->Cin2 : 0;
   p.kchunks2 = (p.Cin2 + 63) / 64;
   bool wave_split = false;
-  if (lin && a->bn <= 0 && a->dbg_pair >= 0 && p.BN == 256 && a->Cout % 128 == 0) {
+  if (lin && !p.splitk && a->bn <= 0 && a->dbg_pair >= 0 && p.BN == 256 && a->Cout % 128 == 0) {
     // wave quantisation on the pair grid (74 clusters): a 256-wide N tile that needs e.g. 1.4 waves
     // costs 2 waves; 128-wide tiles (half the work each) may pack better.  Measured on decode_layer_4
     // (104 pair tiles): BN=256 1153 TF/s, BN=128 1253 TF/s; 128-wide tiles are ~8 % less efficient
@@ -1070,21 +1298,21 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     // two M sub-tiles per CTA (256 pixels, two accumulators sharing every weight tile) when the
     // accumulators fit twice (BN <= 128) and the layer still gives >= 2 waves of tiles
     p.ms = 1;
-    if (a->dbg_ms != 1 && p.BN <= 128 && ((p.NP + 255) / 256) * p.tiles_n >= 2 * device_sm_count()) p.ms = 2;
-    if (a->dbg_ms != 1 && a->dbg_ms != 2 && p.BN <= 64 && ((p.NP + 511) / 512) * p.tiles_n >= 2 * device_sm_count()) p.ms = 4;
-    if (a->dbg_ms == 2 && p.BN <= 128) p.ms = 2;
-    if (a->dbg_ms == 4 && p.BN <= 64) p.ms = 4;
+    if (!p.splitk && a->dbg_ms != 1 && p.BN <= 128 && ((p.NP + 255) / 256) * p.tiles_n >= 2 * device_sm_count()) p.ms = 2;
+    if (!p.splitk && a->dbg_ms != 1 && a->dbg_ms != 2 && p.BN <= 64 && ((p.NP + 511) / 512) * p.tiles_n >= 2 * device_sm_count()) p.ms = 4;
+    if (!p.splitk && a->dbg_ms == 2 && p.BN <= 128) p.ms = 2;
+    if (!p.splitk && a->dbg_ms == 4 && p.BN <= 64) p.ms = 4;
     if (wave_split) p.ms = 1;
     const size_t seg = seg_slot_bytes(p.ms);
     p.tiles_m = (p.NP + 128 * p.ms - 1) / (128 * p.ms);
     // CTA pair (cta_group::2, M = 256) whenever the layer still fills most of the SMs — each CTA then
     // stages only half of every weight tile (measured: dec6 1082 -> 1396 TF/s, dec4 889 -> 1117)
-    p.pair = (a->dbg_pair >= 0 && p.BN >= 64 && p.tiles_m >= 2 &&
+    p.pair = (!p.splitk && a->dbg_pair >= 0 && p.BN >= 64 && p.tiles_m >= 2 &&
               (a->dbg_pair == 1 || p.tiles_m * p.tiles_n >= 96)) ? 1 : 0;
     p.total_tiles = (p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;
     // weight ring: slots of gb tiles; gb = 3 (a whole kernel row per barrier) whenever three tiles
     // (half tiles for a pair) stay <= 48 KB
-    p.gb = (p.pair || (a->dbg_gb != 1 && p.BN <= 144)) ? 3 : 1;
+    p.gb = (p.pair || p.splitk || (a->dbg_gb != 1 && p.BN <= 144)) ? 3 : 1;
     const size_t slot = (p.pair ? b_bytes / 2 : b_bytes) * p.gb;
     const size_t budget = kMaxDynSmem - 1024;
     // One ring round trip costs ~3.1 k cycles whatever the box size (profiles/r1_tma_ring_microbench.md), so
@@ -1096,6 +1324,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     p.nb = static_cast<int>(std::min<size_t>(kMaxRing, (budget - static_cast<size_t>(p.na) * seg) / slot));
     if (p.nb < 2) { vpb_set_error("conv: no room for the weight ring"); return VPB_ERR_ARG; }
     plan->smem_bytes = static_cast<size_t>(p.na) * seg + p.nb * slot + 1024;
+    if (p.splitk) plan->smem_bytes = std::max(plan->smem_bytes, static_cast<size_t>(128) * (p.BN + 4) * 4 + 1024);
     p.TW = 128; p.TH = 1; p.tw_shift = 7;
   } else {
     // spatial tile: minimise padded pixels, prefer wide tiles
@@ -1128,7 +1357,8 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.out_f32 = a->out_f32; p.out_cls = a->out_cls;
   p.trace = a->dbg_trace;
   plan->dtype = a->dtype;
-  plan->grid = p.pair ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
+  plan->grid = p.splitk ? p.total_tiles * p.splitk
+             : p.pair ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
                       : std::min(p.total_tiles, device_sm_count());
   plan->flops = 2.0 * a->H * a->W * static_cast<double>(a->Cout) * a->phases * (a->Cin * a->taps + p.Cin2);
 
@@ -1225,12 +1455,17 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
       VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_lin_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_splitk_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_splitk_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       *done = true;
     }
   }
   const bool bf = plan->dtype == VPB_BF16;
   const dim3 g(plan->grid), b(kThreads);
-  if (plan->p.lin && plan->p.pair) {
+  if (plan->p.lin && plan->p.splitk) {
+    if (bf) VPB_CUDA_OK(launch_k_cluster(conv3x3_splitk_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->p.splitk, plan->mapA, plan->mapB, plan->p));
+    else VPB_CUDA_OK(launch_k_cluster(conv3x3_splitk_kernel<F16>, g, b, plan->smem_bytes, stream, plan->p.splitk, plan->mapA, plan->mapB, plan->p));
+  } else if (plan->p.lin && plan->p.pair) {
     if (bf) VPB_CUDA_OK(launch_k(conv3x3_pair_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
     else VPB_CUDA_OK(launch_k(conv3x3_pair_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
   } else if (plan->p.lin) {

@@ -24,6 +24,7 @@ struct ConvKParams {
   int gb;                        // linear kernel: weight tiles per slot (3 = one kernel row per barrier)
   int ms;                        // linear kernel: M sub-tiles (of 128 pixels) per CTA tile, 1, 2 or 4
   int pair;                      // linear kernel: 1 = CTA-pair kernel (cta_group::2), tiles are pair tiles
+  int splitk;                    // linear kernel: > 1 = split-K kernel, K chunks divided over a cluster of `splitk` CTAs
   int NP, WP, tiles_m;           // linear kernel: padded pixel count, padded width, M tiles
   int in_pad, out_pad, res_pad;  // 1 = that tensor is a zero-bordered image [(H+2)*(W+2)][C]
   uint32_t mg_tn, mg_tw, mg_tpp, mg_wp;  // magic reciprocals (fast_div) of tiles_n, tiles_w, tiles per phase, WP

@@ -89,6 +89,8 @@ typedef struct {
   int Cin2, ld2, in2_pad;
   int dbg_pair;           /* experiment hook, LINEAR kernel: 1 = force the CTA-pair (cta_group::2) kernel,
                              -1 = never use it, 0 = auto */
+  int dbg_splitk;         /* experiment hook, LINEAR kernel: k >= 2 = force the split-K cluster kernel with k CTAs per
+                             tile, -1 = never use it, 0 = auto (small-M layers) */
   unsigned long long* dbg_trace; /* experiment hook, TILE kernel: device buffer [16 tiles][16] of clock64() stamps
                              written by CTA 0 (scripts/trace_tile.py decodes it); NULL = off */
 } vpb_conv_args;

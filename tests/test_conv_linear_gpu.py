@@ -213,3 +213,53 @@ def test_cta_pair_kernel_final_and_residual_modes():
     y = F.gelu(_ref3(x, w, b, 128)).permute(1, 2, 0)
     ref = y * f.float() + f.float()
     assert ((a[1:-1, 1:-1].float() - ref).abs() <= 3e-3 + 1e-3 * ref.abs()).all()
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout,S,bn", [
+    (20, 40, 1280, 768, 0, 0),     # decode_layer_0: auto policy -> 3 CTAs per tile, BN = 128
+    (10, 20, 512, 1280, 0, 0),     # context_layer_6 shape: auto -> 4 CTAs per tile
+    (10, 20, 256, 512, 0, 0),      # context_layer_5 shape: auto -> 2
+    (16, 32, 320, 128, 3, 0),      # 5 K chunks over 3 CTAs (uneven split)
+    (33, 47, 72, 96, 2, 0),        # K tail (64 + 8) and a 96-wide N tile
+    (10, 20, 128, 1456, 2, 0),     # EgoLanes context width: BN = 112, thirteen N tiles
+    (12, 12, 64, 64, 4, 0),        # more CTAs than K chunks -> clamped to 1 chunk each (S = 1 chunk... forced 4 -> kc = 1)
+    (40, 80, 256, 128, 4, 128),    # 27 M tiles, forced
+])
+def test_split_k_cluster_kernel(H, W, Cin, Cout, S, bn):
+    """conv3x3_splitk_kernel: the K loop of one output tile divided over a cluster, partials reduced through
+    distributed shared memory in rank order.  Against torch fp32 and against the unsplit kernel (same
+    products, different fp32 summation order -> equal within rounding of the 16-bit output)."""
+    _setup()
+    from tests.gpu_util import conv_gemm, pad_img
+    x, w, b = _mk(H, W, Cin, Cout, seed=900 + H + Cout)
+    xp = pad_img(x)
+    kw = dict(taps=9, act=L.ACT_GELU, in_pad=1, out_pad=1, algo=L.ALGO_LINEAR, bn=bn)
+    _, _, out = conv_gemm(xp, w, b, splitk=S, **kw)
+    _, _, one = conv_gemm(xp, w, b, splitk=-1, **kw)
+    assert torch.isfinite(out.float()).all(), "border or interior left unwritten"
+    ref = F.gelu(_ref3(x, w, b, Cin)).permute(1, 2, 0)
+    got = out[1:-1, 1:-1, :Cout].float()
+    err = (got - ref).abs()
+    assert (err <= 1.5e-3 + 1e-3 * ref.abs()).all(), err.max().item()
+    assert (got - one[1:-1, 1:-1, :Cout].float()).abs().max() <= 2e-3 + 2e-3 * ref.abs().max()
+    border = out.float().clone()
+    border[1:-1, 1:-1] = 0
+    assert (border == 0).all()
+    # deterministic: same bits on a second run
+    _, _, again = conv_gemm(xp, w, b, splitk=S, **kw)
+    assert torch.equal(out, again)
+
+
+def test_split_k_residual_modes_and_unpadded_output():
+    _setup()
+    from tests.gpu_util import conv_gemm, pad_img
+    x, w, b = _mk(10, 20, 512, 256, seed=5150)
+    f = torch.randn(10, 20, 256).half().cuda()
+    y = F.gelu(_ref3(x, w, b, 512)).permute(1, 2, 0)
+    for mode, ref in ((L.EPI_MULADD, y * f.float() + f.float()), (L.EPI_ADD, y + f.float())):
+        _, _, out = conv_gemm(pad_img(x), w, b, taps=9, act=L.ACT_GELU, mode=mode, res=f, in_pad=1, out_pad=1,
+                              res_pad=0, algo=L.ALGO_LINEAR, splitk=4)
+        assert ((out[1:-1, 1:-1].float() - ref).abs() <= 3e-3 + 1.5e-3 * ref.abs()).all()
+    _, _, flat = conv_gemm(pad_img(x), w, b, taps=9, act=L.ACT_NONE, in_pad=1, out_pad=0, algo=L.ALGO_LINEAR, splitk=2)
+    ref = _ref3(x, w, b, 512).permute(1, 2, 0)
+    assert ((flat.float() - ref).abs() <= 2e-3 + 1e-3 * ref.abs()).all()
