@@ -1221,7 +1221,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
-  // split-K over a cluster for the small-M layers: at most half of the SMs would get a tile at BN = 128
+  // split-K over a cluster for the smallest-M layers (context convs at 10x20: <= 32 tiles at BN = 128)
   p.splitk = 0;
   if (lin && a->mode != VPB_EPI_FINAL && a->dbg_splitk >= 0 && (a->bn <= 0 || a->dbg_splitk >= 2)) {
     int bn = 128;
@@ -1238,7 +1238,9 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     const int kc = (a->Cin + 63) / 64;
     int S = 0;
     if (a->dbg_splitk >= 2) S = std::min(std::min(a->dbg_splitk, 8), kc);
-    else if (a->Cout >= 128 && 2 * tiles <= device_sm_count()) S = std::min(std::min(4, device_sm_count() / tiles), kc / 2);
+    // measured (gpurun_out/bench_conv_v18_splitk.txt): context_layer_6 (30 tiles) 20.1 -> 11.6 us, but the 48-tile
+    // 20x40 layers are faster on the CTA-pair kernel (dec0 36.9 vs 41.9 us) -> only the 10x20 layers
+    else if (a->Cout >= 128 && tiles <= 32) S = std::min(std::min(4, device_sm_count() / tiles), kc / 2);
     if (S >= 2) { p.splitk = S; p.BN = bn; }
   }
   bool convt_fused_bn = false;

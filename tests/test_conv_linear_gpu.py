@@ -216,7 +216,7 @@ def test_cta_pair_kernel_final_and_residual_modes():
 
 
 @pytest.mark.parametrize("H,W,Cin,Cout,S,bn", [
-    (20, 40, 1280, 768, 0, 0),     # decode_layer_0: auto policy -> 3 CTAs per tile, BN = 128
+    (20, 40, 1280, 768, 3, 0),     # decode_layer_0 shape, forced: 3 CTAs per tile, BN = 128
     (10, 20, 512, 1280, 0, 0),     # context_layer_6 shape: auto -> 4 CTAs per tile
     (10, 20, 256, 512, 0, 0),      # context_layer_5 shape: auto -> 2
     (16, 32, 320, 128, 3, 0),      # 5 K chunks over 3 CTAs (uneven split)
