@@ -6,7 +6,7 @@
 //   nn.Conv2d 1x1         scene_neck.py:12,17,22 (skip links) and EfficientNet-B0 pointwise convs
 //   nn.ConvTranspose2d k2 s2   scene_neck.py:11,16,21, scene_seg_head.py:11,16
 //
-// Three main loops share one epilogue.
+// Four main loops share one epilogue.
 //
 // (1) conv_gemm_kernel — "tile" formulation, any of the three op types.
 //     Activations are NHWC 16-bit.  For an output tile of 128 pixels (a TH x TW patch) and BN
@@ -34,6 +34,10 @@
 //     M = 256): each CTA stages its own pixels and HALF of every weight tile.  The dominant kernel
 //     (every 3x3 layer with >= 96 tiles); see the comment above the kernel and
 //     profiles/r1_smem_operand_model.md for why halving the weight operand per SM is what counts.
+//
+// (4) conv3x3_splitk_kernel — formulation (2) with the K chunks of one output tile divided over a
+//     cluster of 2-4 CTAs; fp32 partials are reduced through distributed shared memory in rank order
+//     (deterministic).  Used for the 10x20 context layers (<= 32 output tiles, 36-72 K groups).
 //
 // All: operands land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma reads
 // through descriptors; fp32 accumulators in TMEM, two of them, so the epilogue of tile i overlaps
