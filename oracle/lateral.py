@@ -18,16 +18,25 @@ Reference (read-only, restated, not copied):
       :350-404  fitPoly2ndOrder           -> fit_poly2
       :406-452  calcLaneOffset / calcYawOffset / calcCurvature
 
-Pinning: the reference has no tests or fixtures for this path and cannot be compiled here (needs the
-OpenCV C++ headers).  The third-party arithmetic it calls IS available through the cv2 Python module,
-so tests/test_oracle_lateral.py pins lstsq_poly against cv2.solve(DECOMP_SVD), warp_points against
-cv2.perspectiveTransform and the inverse homography against cv2.invert; the control flow above is a
-line-by-line restatement ("parity unpinned" for that part, stated in DESIGN.md).
+Pinning (two layers):
+  1. Against the reference's OWN sources: oracle/build_ref.py compiles the unmodified lane_filter.cpp,
+     lane_tracking.cpp and estimator.cpp (where they lie under /root/reference) into
+     oracle/_ref/libref_lateral.so with OpenCV's C++ API replaced by the minimal stand-in
+     oracle/cvstub/opencv2/opencv.hpp; tests/test_oracle_lateral_vs_reference.py runs 240 frames of stateful
+     sequences (dropouts, empty / noise-only / single-row masks) through both: validity flags, window counts
+     and BEV points identical, all coefficients and curve parameters within 1e-9.
+  2. The two numeric OpenCV functions the stand-in re-implements are themselves pinned against the real
+     library through its Python binding: lstsq_poly against cv2.solve(DECOMP_SVD) incl. rank-deficient
+     minimum-norm systems, warp_points bit-exact against cv2.perspectiveTransform, the inverse homography
+     against cv2.invert (tests/test_oracle_lateral.py).
+  PathFinder::update needs Eigen (poly_fit.cpp) and stays a restatement built from pinned pieces
+  (fitQuadPoly = lstsq, Estimator::update pinned in layer 1, measurement vector as path_finder.cpp:97-157).
 
 Note on RANSAC (lane_filter.cpp:157-191): `best_inliers` starts as ALL points and a candidate model
 only replaces it when it has strictly MORE inliers than that — impossible — so the loop never changes
 the result and fitPoly is exactly a least-squares fit of all points (order 1 below 30 points, else 2).
-The restatement therefore has no random sampler, and neither has the device kernel.
+The restatement therefore has no random sampler, and neither has the device kernel; layer 1 above confirms
+it (the compiled reference, with its unseeded mt19937, agrees on every frame).
 """
 from __future__ import annotations
 
