@@ -20,17 +20,17 @@ Reference (read-only, restated, not copied):
 
 Pinning (two layers):
   1. Against the reference's OWN sources: oracle/build_ref.py compiles the unmodified lane_filter.cpp,
-     lane_tracking.cpp and estimator.cpp (where they lie under /root/reference) into
-     oracle/_ref/libref_lateral.so with OpenCV's C++ API replaced by the minimal stand-in
-     oracle/cvstub/opencv2/opencv.hpp; tests/test_oracle_lateral_vs_reference.py runs 240 frames of stateful
+     lane_tracking.cpp, estimator.cpp, poly_fit.cpp and path_finder.cpp (where they lie under /root/reference)
+     into oracle/_ref/libref_lateral.so with the OpenCV / Eigen names they use provided by the minimal
+     stand-ins under oracle/cvstub/; tests/test_oracle_lateral_vs_reference.py runs 240 frames of stateful
      sequences (dropouts, empty / noise-only / single-row masks) through both: validity flags, window counts
      and BEV points identical, all coefficients and curve parameters within 1e-9.
   2. The two numeric OpenCV functions the stand-in re-implements are themselves pinned against the real
      library through its Python binding: lstsq_poly against cv2.solve(DECOMP_SVD) incl. rank-deficient
      minimum-norm systems, warp_points bit-exact against cv2.perspectiveTransform, the inverse homography
      against cv2.invert (tests/test_oracle_lateral.py).
-  PathFinder::update needs Eigen (poly_fit.cpp) and stays a restatement built from pinned pieces
-  (fitQuadPoly = lstsq, Estimator::update pinned in layer 1, measurement vector as path_finder.cpp:97-157).
+  PathFinder::update and fitQuadPoly are pinned in layer 1 too (state variances 1e-12, means 1e-3: the
+  reference's predict step adds an unseeded +-1e-5 jitter).
 
 Note on RANSAC (lane_filter.cpp:157-191): `best_inliers` starts as ALL points and a candidate model
 only replaces it when it has strictly MORE inliers than that — impossible — so the loop never changes

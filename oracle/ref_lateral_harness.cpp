@@ -1,7 +1,8 @@
 // TEST INFRASTRUCTURE ONLY — C entry points around the UNMODIFIED reference classes LaneFilter, LaneTracker
 // (VisionPilot/production_release/src/lane_filtering/lane_filter.cpp, src/lane_tracking/lane_tracking.cpp) and
 // Estimator (src/path_planning/estimator.cpp), compiled together with them into oracle/_ref/libref_lateral.so
-// by oracle/build_ref.py.  OpenCV is replaced by oracle/cvstub/opencv2/opencv.hpp.  Used only by
+// by oracle/build_ref.py, plus PathFinder / fitQuadPoly (src/path_planning/path_finder.cpp, poly_fit.cpp).  OpenCV and
+// Eigen are replaced by the stand-ins under oracle/cvstub/.  Used only by
 // tests/test_oracle_lateral_vs_reference.py to pin oracle/lateral.py and oracle/post.py.
 #include <array>
 #include <cstring>
@@ -9,6 +10,8 @@
 #include "lane_filtering/lane_filter.hpp"
 #include "lane_tracking/lane_tracking.hpp"
 #include "path_planning/estimator.hpp"
+#include "path_planning/path_finder.hpp"
+#include "path_planning/poly_fit.hpp"
 
 using namespace autoware_pov::vision::egolanes;
 
@@ -83,6 +86,33 @@ void ref_estimator_update(double* state, const double* meas) {
   e.update(m);
   const auto& r = e.getState();
   for (size_t i = 0; i < STATE_DIM; ++i) { state[2 * i] = r[i].mean; state[2 * i + 1] = r[i].variance; }
+}
+
+// fitQuadPoly + FittedCurve (poly_fit.cpp:26-75): pts = n (x, y) float pairs -> coeff[3], cte, yaw_error
+void ref_fit_quad(const float* pts, int n, double* coeff, double* cte_yaw) {
+  std::vector<cv::Point2f> v;
+  for (int i = 0; i < n; ++i) v.push_back(cv::Point2f(pts[2 * i], pts[2 * i + 1]));
+  auto c = autoware_pov::vision::path_planning::fitQuadPoly(v);
+  autoware_pov::vision::path_planning::FittedCurve fc(c);
+  for (int i = 0; i < 3; ++i) coeff[i] = c[i];
+  cte_yaw[0] = fc.cte; cte_yaw[1] = fc.yaw_error;
+}
+
+void* ref_pathfinder_create(double width) { return new autoware_pov::vision::path_planning::PathFinder(width); }
+void ref_pathfinder_destroy(void* h) { delete static_cast<autoware_pov::vision::path_planning::PathFinder*>(h); }
+// out[0..7] = cte, yaw_error, curvature, lane_width, variances x4; out[8] = fused_valid; state = [14][2]
+void ref_pathfinder_update(void* h, const float* left, int nl, const float* right, int nr, double steering, double* out,
+                           double* state) {
+  auto* pf = static_cast<autoware_pov::vision::path_planning::PathFinder*>(h);
+  std::vector<cv::Point2f> l, r;
+  for (int i = 0; i < nl; ++i) l.push_back(cv::Point2f(left[2 * i], left[2 * i + 1]));
+  for (int i = 0; i < nr; ++i) r.push_back(cv::Point2f(right[2 * i], right[2 * i + 1]));
+  auto o = pf->update(l, r, steering);
+  out[0] = o.cte; out[1] = o.yaw_error; out[2] = o.curvature; out[3] = o.lane_width;
+  out[4] = o.cte_variance; out[5] = o.yaw_variance; out[6] = o.curv_variance; out[7] = o.lane_width_variance;
+  out[8] = o.fused_valid ? 1.0 : 0.0;
+  const auto& st = pf->getState();
+  for (size_t i = 0; i < STATE_DIM; ++i) { state[2 * i] = st[i].mean; state[2 * i + 1] = st[i].variance; }
 }
 
 }  // extern "C"

@@ -131,3 +131,62 @@ def test_estimator_update_matches_reference(ref):
         ref.ref_estimator_update(want.ctypes.data, m.ctypes.data)
         got = post.estimator_update(st, ms)
         np.testing.assert_allclose(got, want, rtol=1e-13, atol=0, equal_nan=True)
+
+
+def test_fit_quad_poly_and_fitted_curve_match_reference(ref):
+    """fitQuadPoly (Eigen colPivHouseholderQr, poly_fit.cpp:36-75) and FittedCurve (:26-34) vs oracle/post.py."""
+    ref.ref_fit_quad.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(21)
+    for n in (0, 2, 3, 5, 40, 130):
+        ys = np.sort(rng.uniform(0, 40, n)).astype(np.float32)
+        xs = (0.002 * ys ** 2 - 0.05 * ys + rng.normal(1.8, 0.05, n)).astype(np.float32)
+        pts = np.ascontiguousarray(np.stack([xs, ys], 1), dtype=np.float32)
+        coeff, cy = np.zeros(3), np.zeros(2)
+        ref.ref_fit_quad(pts.ctypes.data, n, coeff.ctypes.data, cy.ctypes.data)
+        got = post.polyfit(xs, ys, 2)
+        if n <= 2:
+            assert np.isnan(coeff).all() and np.isnan(got).all() and np.isnan(cy).all()
+            continue
+        np.testing.assert_allclose(got, coeff, rtol=1e-8, atol=1e-10)
+        cte, yaw = post.fitted_curve(coeff)
+        np.testing.assert_allclose([cte, yaw], cy, rtol=1e-13)
+
+
+def test_pathfinder_update_matches_reference(ref):
+    """PathFinder::update (path_finder.cpp:48-181) over a 30-frame sequence with missing lines.  The reference adds
+    an unseeded U(-1e-5, 1e-5) to every state mean in its predict step, the restatement adds 0: means agree to
+    1e-3, variances (deterministic) to 1e-12."""
+    ref.ref_pathfinder_create.restype = C.c_void_p
+    ref.ref_pathfinder_create.argtypes = [C.c_double]
+    ref.ref_pathfinder_destroy.argtypes = [C.c_void_p]
+    ref.ref_pathfinder_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p,
+                                          C.c_void_p]
+    h = ref.ref_pathfinder_create(4.0)
+    pf = LT.PathFinder(4.0)
+    rng = np.random.default_rng(33)
+    try:
+        for k in range(30):
+            ys = np.arange(250, 640, 13, dtype=np.float32)
+            left = np.stack([288 + 0.02 * (640 - ys) + rng.normal(0, 0.5, len(ys)), ys], 1).astype(np.float32)
+            right = np.stack([352 + 0.02 * (640 - ys) + rng.normal(0, 0.5, len(ys)), ys], 1).astype(np.float32)
+            if k in (7, 8):
+                left = left[:2]                    # <= 2 points: NaN fit, "left missing" branch
+            if k == 15:
+                right = right[:0]
+            if k == 20:
+                left, right = left[:1], right[:2]  # both missing -> default width
+            steer = 0.01 * k
+            lm, rm = LT.pixels_to_meters(left), LT.pixels_to_meters(right)
+            lm, rm = np.ascontiguousarray(lm), np.ascontiguousarray(rm)
+            out, state = np.zeros(9), np.zeros((14, 2))
+            ref.ref_pathfinder_update(h, lm.ctypes.data, len(lm), rm.ctypes.data, len(rm), steer, out.ctypes.data,
+                                      state.ctypes.data)
+            got = pf.update(left, right, steer)
+            np.testing.assert_allclose(pf.state[:, 1], state[:, 1], rtol=1e-12, err_msg=f"variances, frame {k}")
+            np.testing.assert_allclose(pf.state[:, 0], state[:, 0], rtol=0, atol=1e-3, err_msg=f"means, frame {k}")
+            np.testing.assert_allclose([got["cte"], got["yaw_error"], got["lane_width"]], out[[0, 1, 3]], atol=1e-3)
+            np.testing.assert_allclose([got["cte_variance"], got["yaw_variance"], got["curv_variance"],
+                                        got["lane_width_variance"]], out[4:8], rtol=1e-12)
+            assert got["curvature"] == out[2] and bool(out[8]) == got["fused_valid"]
+    finally:
+        ref.ref_pathfinder_destroy(h)
