@@ -190,3 +190,43 @@ def test_pathfinder_update_matches_reference(ref):
             assert got["curvature"] == out[2] and bool(out[8]) == got["fused_valid"]
     finally:
         ref.ref_pathfinder_destroy(h)
+
+
+def test_random_single_frames_match_reference(ref):
+    """300 independent random frames (fresh filter / tracker each): sparse noise of varying density, random line
+    segments, blobs — exercises start-point search, window clamping at the image borders and the fit order switch."""
+    rng = np.random.default_rng(777)
+    for k in range(300):
+        m = np.zeros((3, 80, 160), np.float32)
+        for _ in range(int(rng.integers(0, 6))):            # random straight segments in random channels
+            ch = int(rng.integers(0, 3))
+            x0, x1 = rng.uniform(0, 160, 2)
+            y0, y1 = rng.uniform(20, 80, 2)
+            n = int(max(abs(x1 - x0), abs(y1 - y0))) + 1
+            xs = np.clip(np.round(np.linspace(x0, x1, n)).astype(int), 0, 159)
+            ys = np.clip(np.round(np.linspace(y0, y1, n)).astype(int), 0, 79)
+            m[ch, ys, xs] = 1.0
+            if rng.uniform() < 0.5:
+                m[ch, ys, np.clip(xs + 1, 0, 159)] = 1.0
+        m[rng.uniform(size=m.shape) < rng.uniform(0, 0.02)] = 1.0
+        h = ref.ref_lateral_create(0.5)
+        try:
+            o = RefOut()
+            ref.ref_lateral_update(h, m.ctypes.data, 80, 160, 1920, 1080, C.byref(o))
+        finally:
+            ref.ref_lateral_destroy(h)
+        fo = LT.LaneFilter(0.5).update(m)
+        tr = LT.LaneTracker().update(fo.left, fo.right)
+        assert bool(o.filt_left_valid) == (fo.left is not None) and bool(o.filt_right_valid) == (fo.right is not None), k
+        sl, sr = LT.find_starting_points(m)
+        nl = len(LT.sliding_window_search(m, sl, True)[1]) if sl else 0
+        nr = len(LT.sliding_window_search(m, sr, False)[1]) if sr else 0
+        assert (o.n_left_windows, o.n_right_windows) == (nl, nr), k
+        if fo.left is not None:
+            np.testing.assert_allclose(np.array(o.filt_left), fo.left, rtol=1e-8, atol=1e-8, err_msg=str(k))
+        if fo.right is not None:
+            np.testing.assert_allclose(np.array(o.filt_right), fo.right, rtol=1e-8, atol=1e-8, err_msg=str(k))
+        assert bool(o.bev_valid) == tr.bev_valid, k
+        if tr.bev_valid:
+            np.testing.assert_allclose([o.lane_offset, o.yaw_offset, o.curvature], [tr.lane_offset, tr.yaw_offset, tr.curvature],
+                                       rtol=1e-8, atol=1e-8, err_msg=str(k))
