@@ -68,7 +68,8 @@ class LateralOut(C.Structure):
                 ("pf_cte", C.c_double), ("pf_yaw_error", C.c_double), ("pf_curvature", C.c_double),
                 ("pf_lane_width", C.c_double), ("pf_cte_variance", C.c_double), ("pf_yaw_variance", C.c_double),
                 ("pf_curv_variance", C.c_double), ("pf_lane_width_variance", C.c_double),
-                ("pf_fused_valid", C.c_int), ("pf_ran", C.c_int)]
+                ("pf_fused_valid", C.c_int), ("pf_ran", C.c_int),
+                ("pf_meas", (C.c_double * 2) * 14)]
 
 
 _lib = None

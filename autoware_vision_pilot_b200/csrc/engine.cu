@@ -40,6 +40,9 @@ static int load_vpw(const char* path, WeightMap& out) {
   FILE* fp = fopen(path, "rb");
   if (!fp) { vpb_set_error("cannot open weight file '%s'", path); return VPB_ERR_IO; }
   auto fail = [&](const char* why) { fclose(fp); vpb_set_error("%s: %s", path, why); return VPB_ERR_IO; };
+  if (fseek(fp, 0, SEEK_END) != 0) return fail("cannot seek");
+  const long file_size = ftell(fp);
+  rewind(fp);
   char magic[4]; uint32_t n = 0;
   if (fread(magic, 1, 4, fp) != 4 || memcmp(magic, "VPW1", 4) != 0) return fail("not a VPW1 file");
   if (fread(&n, 4, 1, fp) != 1 || n > 100000) return fail("bad tensor count");
@@ -52,13 +55,22 @@ static int load_vpw(const char* path, WeightMap& out) {
     HostTensor t; t.dims.resize(nd);
     for (uint32_t d = 0; d < nd; ++d) { uint32_t v; if (fread(&v, 4, 1, fp) != 1) return fail("bad dims"); t.dims[d] = static_cast<int>(v); }
     if (fread(&nb, 8, 1, fp) != 1) return fail("bad size");
-    const size_t ne = t.numel();
+    size_t ne = 1;
+    bool dims_ok = true;
+    for (int d : t.dims) {                                   // bounded: no overflow, no absurd allocation
+      if (d < 0 || (d > 0 && ne > (static_cast<size_t>(1) << 31) / static_cast<size_t>(d))) { dims_ok = false; break; }
+      ne *= static_cast<size_t>(d);
+    }
+    if (!dims_ok) return fail("tensor dims out of range");
     if (dt == 0) {
       if (nb != ne * 4) return fail("f32 size mismatch");
       t.f.resize(ne);
       if (ne && fread(t.f.data(), 4, ne, fp) != ne) return fail("truncated data");
     } else {
-      if (fseek(fp, static_cast<long>(nb), SEEK_CUR) != 0) return fail("truncated data");  // num_batches_tracked: ignored
+      // num_batches_tracked (int64 scalar): skipped, but the payload must really be there
+      const long here = ftell(fp);
+      if (here < 0 || nb > static_cast<uint64_t>(file_size - here) || fseek(fp, static_cast<long>(nb), SEEK_CUR) != 0)
+        return fail("truncated data");
     }
     out[name] = std::move(t);
   }
@@ -118,8 +130,18 @@ static Prefixes prefixes_for(int kind) {
 
 using namespace vpb;
 
+// RAII: make the engine's device current for the duration of a C-ABI call and restore the caller's
+// device afterwards (several engines / threads / GPUs may share one process).
+struct DeviceGuard {
+  int prev = -1; bool changed = false;
+  explicit DeviceGuard(int d) { if (cudaGetDevice(&prev) == cudaSuccess && prev != d) changed = cudaSetDevice(d) == cudaSuccess; }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
 struct vp_engine {
   vp_engine_config cfg{};
+  int gpu_id = 0;
+  bool oom = false;                       // a device / pinned allocation failed during construction
   int dtype = VPB_F16;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -133,6 +155,7 @@ struct vp_engine {
   uint8_t* h_frame = nullptr; size_t h_frame_cap = 0;
   void* d_pre = nullptr;                  // [320][640][4]
   uint8_t* d_resized = nullptr;           // optional uint8 resized image (tap "resized")
+  float* d_tap_scratch = nullptr; size_t tap_scratch_cap = 0;   // vp_engine_read_tap staging (grown on demand)
   std::vector<ModelOut> outs;
   std::map<std::string, Tens> taps;
   int shared_encoders = 0, shared_trunks = 0;
@@ -169,6 +192,8 @@ struct vp_engine {
   std::vector<cudaEvent_t> lane_done;
 
   ~vp_engine() {
+    DeviceGuard guard(gpu_id);
+    if (d_tap_scratch) cudaFree(d_tap_scratch);
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
     for (size_t i = 1; i < lane_streams.size(); ++i) if (lane_streams[i]) cudaStreamDestroy(lane_streams[i]);
@@ -183,7 +208,14 @@ struct vp_engine {
   // ---------------------------------------------------------- allocation / upload helpers
   void* dalloc(size_t bytes, bool is_weight) {
     void* p = nullptr;
-    if (cudaMalloc(&p, std::max<size_t>(bytes, 256)) != cudaSuccess) return nullptr;
+    const cudaError_t ce = cudaMalloc(&p, std::max<size_t>(bytes, 256));
+    if (ce != cudaSuccess || !p) {
+      // sticky: vp_engine_create reports it (uploads below skip NULL, nothing is launched during construction)
+      if (!oom) vpb_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(ce));
+      oom = true;
+      cudaGetLastError();
+      return nullptr;
+    }
     cudaMemset(p, 0, std::max<size_t>(bytes, 256));
     dev_allocs.push_back(p);
     (is_weight ? weight_bytes : act_bytes) += bytes;
@@ -255,10 +287,27 @@ static const HostTensor* find_w(const WeightMap& w, const std::string& key) {
   return &it->second;
 }
 
+// Every tensor's shape is checked against what the architecture expects before it is indexed: a checkpoint
+// of another variant, or a truncated / corrupt file, fails with VPB_ERR_IO instead of reading out of bounds.
+static const HostTensor* find_w_shaped(const WeightMap& w, const std::string& key, std::initializer_list<int> dims) {
+  const HostTensor* t = find_w(w, key);
+  if (!t) return nullptr;
+  bool ok = t->dims.size() == dims.size() && t->f.size() == t->numel();
+  if (ok) { size_t i = 0; for (int d : dims) { if (d >= 0 && t->dims[i] != d) ok = false; ++i; } }
+  if (!ok) {
+    std::string got, want;
+    for (int d : t->dims) got += std::to_string(d) + ",";
+    for (int d : dims) want += (d < 0 ? std::string("*") : std::to_string(d)) + ",";
+    vpb_set_error("weight '%s' has shape [%s] but this architecture needs [%s]", key.c_str(), got.c_str(), want.c_str());
+    return nullptr;
+  }
+  return t;
+}
+
 // BatchNorm folding (eval mode, eps 1e-5 — torchvision EfficientNet-B0): y = conv(x)*s + t
 static bool bn_fold(const WeightMap& w, const std::string& p, int C, std::vector<float>& s, std::vector<float>& t) {
-  const HostTensor *g = find_w(w, p + "weight"), *b = find_w(w, p + "bias"),
-                   *m = find_w(w, p + "running_mean"), *v = find_w(w, p + "running_var");
+  const HostTensor *g = find_w_shaped(w, p + "weight", {C}), *b = find_w_shaped(w, p + "bias", {C}),
+                   *m = find_w_shaped(w, p + "running_mean", {C}), *v = find_w_shaped(w, p + "running_var", {C});
   if (!g || !b || !m || !v) return false;
   s.resize(C); t.resize(C);
   for (int c = 0; c < C; ++c) {
@@ -300,7 +349,7 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
   const int dt = e.dtype;
   std::vector<float> s, t;
   // stem
-  const HostTensor* sw = find_w(w, p + "0.0.weight");
+  const HostTensor* sw = find_w_shaped(w, p + "0.0.weight", {32, 3, 3, 3});
   if (!sw || !bn_fold(w, p + "0.1.", 32, s, t)) return VPB_ERR_IO;
   std::vector<float> stem(27 * 32);
   for (int co = 0; co < 32; ++co)
@@ -326,7 +375,7 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
       int bi = 0;
       Tens cur = x;
       if (exp != 1) {  // 1x1 expand + BN + SiLU -> tcgen05 GEMM
-        const HostTensor* ew = find_w(w, bp + "0.0.weight");
+        const HostTensor* ew = find_w_shaped(w, bp + "0.0.weight", {ce, ci, 1, 1});
         if (!ew || !bn_fold(w, bp + "0.1.", ce, s, t)) return VPB_ERR_IO;
         void* dw_ = e.upload_16(pack_conv(*ew, &s));
         float* db = e.upload_f32(t);
@@ -336,7 +385,7 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
         cur = ex; bi = 1;
       }
       // depthwise + BN + SiLU (+ SE pooling partial sums)
-      const HostTensor* dwt = find_w(w, bp + std::to_string(bi) + ".0.weight");
+      const HostTensor* dwt = find_w_shaped(w, bp + std::to_string(bi) + ".0.weight", {ce, 1, k, k});
       if (!dwt || !bn_fold(w, bp + std::to_string(bi) + ".1.", ce, s, t)) return VPB_ERR_IO;
       std::vector<float> dwp(static_cast<size_t>(k) * k * ce);
       for (int c = 0; c < ce; ++c)
@@ -353,9 +402,9 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
       }
       // SE gate folded into the projection weights
       const std::string sp = bp + std::to_string(bi + 1) + ".";
-      const HostTensor *f1 = find_w(w, sp + "fc1.weight"), *b1 = find_w(w, sp + "fc1.bias"),
-                       *f2 = find_w(w, sp + "fc2.weight"), *b2 = find_w(w, sp + "fc2.bias");
-      const HostTensor* pw = find_w(w, bp + std::to_string(bi + 2) + ".0.weight");
+      const HostTensor *f1 = find_w_shaped(w, sp + "fc1.weight", {sq, ce, 1, 1}), *b1 = find_w_shaped(w, sp + "fc1.bias", {sq}),
+                       *f2 = find_w_shaped(w, sp + "fc2.weight", {ce, sq, 1, 1}), *b2 = find_w_shaped(w, sp + "fc2.bias", {ce});
+      const HostTensor* pw = find_w_shaped(w, bp + std::to_string(bi + 2) + ".0.weight", {cout, ce, 1, 1});
       if (!f1 || !b1 || !f2 || !b2 || !pw || !bn_fold(w, bp + std::to_string(bi + 2) + ".1.", cout, s, t)) return VPB_ERR_IO;
       std::vector<float> f2t(f2->f.size());   // fc2 [C][sq] -> [sq][C] so the gate kernel reads it coalesced
       for (int c = 0; c < ce; ++c)
@@ -385,7 +434,7 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
     stage_out[si + 1] = x;
   }
   // encoder[8]: 1x1 320 -> 1280 + BN + SiLU
-  const HostTensor* hw = find_w(w, p + "8.0.weight");
+  const HostTensor* hw = find_w_shaped(w, p + "8.0.weight", {1280, 320, 1, 1});
   if (!hw || !bn_fold(w, p + "8.1.", 1280, s, t)) return VPB_ERR_IO;
   void* d_hw = e.upload_16(pack_conv(*hw, &s));
   float* d_hb = e.upload_f32(t);
@@ -398,8 +447,9 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
 
 static int conv_layer(vp_engine& e, const WeightMap& w, const std::string& key, const std::string& name,
                       const Tens& in, int taps, int act, int mode, Tens* out, const Tens* res) {
-  const HostTensor *wt = find_w(w, key + ".weight"), *bt = find_w(w, key + ".bias");
-  if (!wt || !bt) return VPB_ERR_IO;
+  const HostTensor* wt = find_w_shaped(w, key + ".weight", {-1, -1, 3, 3});
+  const HostTensor* bt = wt ? find_w_shaped(w, key + ".bias", {wt->dims[0]}) : nullptr;
+  if (!wt || !bt || taps != 9) return VPB_ERR_IO;
   const int Cout = wt->dims[0];
   if (wt->dims[1] != in.C) { vpb_set_error("%s: Cin %d != input channels %d", key.c_str(), wt->dims[1], in.C); return VPB_ERR_ARG; }
   void* dw_ = e.upload_16(pack_conv(*wt, nullptr));
@@ -412,7 +462,8 @@ static int conv_layer(vp_engine& e, const WeightMap& w, const std::string& key, 
 static int up_skip(vp_engine& e, const WeightMap& w, const std::string& p, int i, const std::string& tag,
                    const Tens& in, const Tens* skip, Tens* out) {
   const std::string uk = p + "upsample_layer_" + std::to_string(i);
-  const HostTensor *ut = find_w(w, uk + ".weight"), *ub = find_w(w, uk + ".bias");
+  const HostTensor* ut = find_w_shaped(w, uk + ".weight", {in.C, -1, 2, 2});
+  const HostTensor* ub = ut ? find_w_shaped(w, uk + ".bias", {ut->dims[1]}) : nullptr;
   if (!ut || !ub) return VPB_ERR_IO;
   const int Cout = ut->dims[1];
   *out = e.act_alloc(in.H * 2, in.W * 2, Cout, /*pad=*/1);
@@ -423,7 +474,7 @@ static int up_skip(vp_engine& e, const WeightMap& w, const std::string& p, int i
   // the skip link's 1x1 conv is a second K segment of the same GEMM: both layers accumulate in the
   // fp32 TMEM accumulator and the sum is rounded and written once (no intermediate tensor)
   const std::string sk = p + "skip_link_layer_" + std::to_string(i);
-  const HostTensor *st = find_w(w, sk + ".weight"), *sb = find_w(w, sk + ".bias");
+  const HostTensor *st = find_w_shaped(w, sk + ".weight", {Cout, -1, 1, 1}), *sb = find_w_shaped(w, sk + ".bias", {Cout});
   if (!st || !sb) return VPB_ERR_IO;
   if (st->dims[0] != Cout || st->dims[1] != skip->C || (skip->C & 7)) {
     vpb_set_error("%s: skip link [%d,%d] does not match Cout=%d / skip channels %d", sk.c_str(), st->dims[0],
@@ -451,7 +502,7 @@ static int build_context(vp_engine& e, const WeightMap& w, const std::string& p,
   float* cur = d_v;
   for (int i = 0; i < 3; ++i) {
     const std::string k = p + "context_layer_" + std::to_string(i);
-    const HostTensor *wt = find_w(w, k + ".weight"), *bt = find_w(w, k + ".bias");
+    const HostTensor *wt = find_w_shaped(w, k + ".weight", {dims[i + 1], dims[i]}), *bt = find_w_shaped(w, k + ".bias", {dims[i + 1]});
     if (!wt || !bt) return VPB_ERR_IO;
     float *dw_ = e.upload_f32(wt->f), *db = e.upload_f32(bt->f);
     float* y = static_cast<float*>(e.dalloc(dims[i + 1] * 4, false));
@@ -461,7 +512,7 @@ static int build_context(vp_engine& e, const WeightMap& w, const std::string& p,
              2.0 * in_f * out_f);
     cur = y;
   }
-  const HostTensor *w3 = find_w(w, p + "context_layer_3.weight"), *b3 = find_w(w, p + "context_layer_3.bias");
+  const HostTensor *w3 = find_w_shaped(w, p + "context_layer_3.weight", {128, 1, 3, 3}), *b3 = find_w_shaped(w, p + "context_layer_3.bias", {128});
   if (!w3 || !b3) return VPB_ERR_IO;
   float *d_w3 = e.upload_f32(w3->f), *d_b3 = e.upload_f32(b3->f);
   Tens c4 = e.act_alloc(feat.H, feat.W, 128, /*pad=*/1);
@@ -500,7 +551,8 @@ static int build_neck(vp_engine& e, const WeightMap& w, const std::string& p, co
 
 static int final_conv(vp_engine& e, const WeightMap& w, const std::string& key, const std::string& name,
                       const Tens& in, int final_kind, ModelOut& mo) {
-  const HostTensor *wt = find_w(w, key + ".weight"), *bt = find_w(w, key + ".bias");
+  const HostTensor* wt = find_w_shaped(w, key + ".weight", {-1, in.C, 3, 3});
+  const HostTensor* bt = wt ? find_w_shaped(w, key + ".bias", {wt->dims[0]}) : nullptr;
   if (!wt || !bt) return VPB_ERR_IO;
   const int Cout = wt->dims[0];
   void* dw_ = e.upload_16(pack_conv(*wt, nullptr));
@@ -718,7 +770,11 @@ extern "C" int vp_engine_create(const vp_engine_config* cfg, vp_engine** out) {
     vpb_set_error("vp_engine_create: no CUDA device (this engine has no CPU fallback)");
     return VPB_ERR_CUDA;
   }
-  VPB_CUDA_OK(cudaSetDevice(cfg->gpu_id));
+  if (cfg->gpu_id < 0 || cfg->gpu_id >= ndev) {
+    vpb_set_error("vp_engine_create: gpu_id %d out of range (%d devices)", cfg->gpu_id, ndev);
+    return VPB_ERR_ARG;
+  }
+  DeviceGuard guard(cfg->gpu_id);
   cudaDeviceProp prop;
   VPB_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->gpu_id));
   if (prop.major != 10) {
@@ -727,6 +783,7 @@ extern "C" int vp_engine_create(const vp_engine_config* cfg, vp_engine** out) {
   }
   std::unique_ptr<vp_engine> e(new vp_engine());
   e->cfg = *cfg;
+  e->gpu_id = cfg->gpu_id;
   e->dtype = cfg->dtype == VPB_BF16 ? VPB_BF16 : VPB_F16;
   if (cfg->stream) e->stream = static_cast<cudaStream_t>(cfg->stream);
   else { VPB_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
@@ -746,19 +803,22 @@ extern "C" int vp_engine_create(const vp_engine_config* cfg, vp_engine** out) {
     int rc = load_vpw(cfg->weights[i], w);
     if (rc) return rc;
     rc = build_model(*e, i, cfg->kinds[i], w);
+    if (e->oom) return VPB_ERR_CUDA;       // message set by the failing allocation
     if (rc) return rc;
   }
+  if (e->oom) return VPB_ERR_CUDA;
   VPB_CUDA_OK(cudaDeviceSynchronize());
   *out = e.release();
   return VPB_OK;
 }
 
-extern "C" void vp_engine_destroy(vp_engine* e) { delete e; }
+extern "C" void vp_engine_destroy(vp_engine* e) { delete e; }   // ~vp_engine switches to the engine's device
 
 extern "C" int vp_engine_num_models(const vp_engine* e) { return e ? static_cast<int>(e->outs.size()) : 0; }
 
 extern "C" uint8_t* vp_engine_pinned_frame(vp_engine* e, size_t bytes) {
   if (!e) return nullptr;
+  DeviceGuard guard(e->gpu_id);
   if (bytes > e->h_frame_cap) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { vpb_set_error("cudaMallocHost(%zu) failed", bytes); return nullptr; }
@@ -770,11 +830,13 @@ extern "C" uint8_t* vp_engine_pinned_frame(vp_engine* e, size_t bytes) {
 
 extern "C" int vp_engine_infer_device(vp_engine* e, const uint8_t* frame_dev, int h, int w, int stride) {
   if (!e || !frame_dev || h <= 0 || w <= 0 || stride < w * 3) { vpb_set_error("vp_engine_infer_device: bad arguments"); return VPB_ERR_ARG; }
+  DeviceGuard guard(e->gpu_id);
   return enqueue_frame(*e, frame_dev, h, w, stride);
 }
 
 extern "C" int vp_engine_sync(vp_engine* e) {
   if (!e) return VPB_ERR_ARG;
+  DeviceGuard guard(e->gpu_id);
   VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
   return VPB_OK;
 }
@@ -791,11 +853,16 @@ extern "C" int vp_engine_submit(vp_engine* e, const uint8_t* frame_host, int h, 
 
 static int submit_host_frame(vp_engine* e, const uint8_t* frame_host, int h, int w, int stride, bool sync) {
   if (!e || !frame_host || h <= 0 || w <= 0 || stride < w * 3) { vpb_set_error("vp_engine_infer: bad arguments"); return VPB_ERR_ARG; }
-  const size_t bytes = static_cast<size_t>(h) * stride;
+  DeviceGuard guard(e->gpu_id);
+  // The device copy is tightly packed (pitch w*3): only the w*3 valid bytes of every row are read from the
+  // caller's buffer, so a cv::Mat ROI / strided view is never read past its last row's end.
+  const int dpitch = w * 3;
+  const size_t bytes = static_cast<size_t>(h) * dpitch;
   int rc = ensure_frame_buffers(*e, bytes);
   if (rc) return rc;
-  VPB_CUDA_OK(cudaMemcpyAsync(e->d_frame, frame_host, bytes, cudaMemcpyHostToDevice, e->stream));
-  rc = enqueue_frame(*e, e->d_frame, h, w, stride);
+  if (stride == dpitch) VPB_CUDA_OK(cudaMemcpyAsync(e->d_frame, frame_host, bytes, cudaMemcpyHostToDevice, e->stream));
+  else VPB_CUDA_OK(cudaMemcpy2DAsync(e->d_frame, dpitch, frame_host, stride, dpitch, h, cudaMemcpyHostToDevice, e->stream));
+  rc = enqueue_frame(*e, e->d_frame, h, w, dpitch);
   if (rc) return rc;
   for (auto& mo : e->outs) {
     if (mo.has_cls)
@@ -809,6 +876,7 @@ static int submit_host_frame(vp_engine* e, const uint8_t* frame_host, int h, int
 
 extern "C" int vp_engine_fetch_raw(vp_engine* e, int idx) {
   if (!e || idx < 0 || idx >= static_cast<int>(e->outs.size())) return VPB_ERR_ARG;
+  DeviceGuard guard(e->gpu_id);
   auto& mo = e->outs[idx];
   VPB_CUDA_OK(cudaMemcpyAsync(mo.h_raw, mo.d_raw, static_cast<size_t>(mo.C) * mo.H * mo.W * 4, cudaMemcpyDeviceToHost, e->stream));
   if (mo.has_cls)
@@ -842,6 +910,7 @@ extern "C" int vp_engine_get_stats(const vp_engine* e, vp_engine_stats* s) {
 extern "C" int vp_engine_profile(vp_engine* e, int max_ops, float* ms, double* flops, const char** names, int* is_gemm, int* n_ops) {
   if (!e || !ms || !n_ops) return VPB_ERR_ARG;
   if (!e->g_src) { vpb_set_error("vp_engine_profile: run one inference first"); return VPB_ERR_STATE; }
+  DeviceGuard guard(e->gpu_id);
   const int n = static_cast<int>(e->ops.size()) + 1;
   *n_ops = n;
   if (n > max_ops) { vpb_set_error("vp_engine_profile: need room for %d ops", n); return VPB_ERR_ARG; }
@@ -872,6 +941,7 @@ extern "C" int vp_engine_profile(vp_engine* e, int max_ops, float* ms, double* f
 extern "C" int vp_engine_time_kind(vp_engine* e, int kind, int reps, float* ms, double* flops, int* launches) {
   if (!e || !ms || reps <= 0) return VPB_ERR_ARG;
   if (!e->g_src) { vpb_set_error("vp_engine_time_kind: run one inference first"); return VPB_ERR_STATE; }
+  DeviceGuard guard(e->gpu_id);
   cudaEvent_t a, b;
   VPB_CUDA_OK(cudaEventCreate(&a));
   VPB_CUDA_OK(cudaEventCreate(&b));
@@ -897,6 +967,7 @@ extern "C" int vp_engine_time_kind(vp_engine* e, int kind, int reps, float* ms, 
 
 extern "C" int vp_engine_read_resized(vp_engine* e, uint8_t* dst) {
   if (!e || !dst) return VPB_ERR_ARG;
+  DeviceGuard guard(e->gpu_id);
   VPB_CUDA_OK(cudaMemcpyAsync(dst, e->d_resized, static_cast<size_t>(kNetH) * kNetW * 3, cudaMemcpyDeviceToHost, e->stream));
   VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
   return VPB_OK;
@@ -923,14 +994,30 @@ extern "C" long vp_engine_read_tap(vp_engine* e, const char* name, float* dst, l
   if (c) *c = Cv; if (h) *h = a.H; if (w) *w = a.W;
   if (!dst) return n;
   if (cap < n) { vpb_set_error("tap buffer too small"); return VPB_ERR_ARG; }
-  float* d = nullptr;
-  VPB_CUDA_OK(cudaMalloc(&d, n * 4));
+  DeviceGuard guard(e->gpu_id);
+  if (static_cast<size_t>(n) > e->tap_scratch_cap) {       // staging buffer kept by the engine, grown on demand
+    if (e->d_tap_scratch) { cudaFree(e->d_tap_scratch); e->d_tap_scratch = nullptr; e->tap_scratch_cap = 0; }
+    VPB_CUDA_OK(cudaMalloc(&e->d_tap_scratch, static_cast<size_t>(n) * 4));
+    e->tap_scratch_cap = static_cast<size_t>(n);
+  }
+  float* d = e->d_tap_scratch;
   const int blocks = static_cast<int>((n + 255) / 256);
   if (e->dtype == VPB_BF16) tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __nv_bfloat16*>(a.p), a.H, a.W, a.C, Cv, a.pad, d);
   else tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __half*>(a.p), a.H, a.W, a.C, Cv, a.pad, d);
   cudaError_t ce = cudaMemcpyAsync(dst, d, n * 4, cudaMemcpyDeviceToHost, e->stream);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-  cudaFree(d);
   if (ce != cudaSuccess) { vpb_set_error("read_tap: %s", cudaGetErrorString(ce)); return VPB_ERR_CUDA; }
   return n;
 }
+
+extern "C" int vp_engine_tap_dev(vp_engine* e, const char* name, vp_tap_view* v) {
+  if (!e || !name || !v) return VPB_ERR_ARG;
+  auto it = e->taps.find(name);
+  if (it == e->taps.end()) { vpb_set_error("no tap '%s'", name); return VPB_ERR_ARG; }
+  const Tens& a = it->second;
+  v->data = a.p; v->height = a.H; v->width = a.W; v->channels = a.C; v->ld = a.C; v->pad = a.pad;
+  v->dtype = e->dtype;
+  return VPB_OK;
+}
+
+extern "C" void* vp_engine_stream(vp_engine* e) { return e ? static_cast<void*>(e->stream) : nullptr; }

@@ -421,6 +421,10 @@ __global__ void __launch_bounds__(256) lateral_kernel(const float* __restrict__ 
 
   vpb_lateral_out o;
   memset(&o, 0, sizeof(o));
+  for (int i = 0; i < 14; ++i) {                       // "no measurement" unless PathFinder runs below
+    o.pf_meas[i][0] = nan("");
+    o.pf_meas[i][1] = (i >= 4 && i < 8) || i >= 12 ? 0.01 * 0.01 : 0.1 * 0.1;
+  }
   if (nl > 0 && nr > 0) {
     const int n = min(nl, nr);
     for (int k = lane; k < n; k += 32) {
@@ -479,6 +483,7 @@ __global__ void __launch_bounds__(256) lateral_kernel(const float* __restrict__ 
     if (isnan(cte[0]) && isnan(cte[1])) mm[12] = 4.0;
     else if (isnan(cte[0]) || isnan(cte[1])) mm[12] = w12;
     else mm[12] = cte[1] - cte[0];
+    for (int i = 0; i < 14; ++i) { o.pf_meas[i][0] = mm[i]; o.pf_meas[i][1] = mv[i]; }
     for (int i = 0; i < 14; ++i) {                     // Estimator::update (estimator.cpp:24-74)
       const double v0 = pf[i][1], m0 = pf[i][0];
       if (isnan(mm[i])) { pf[i][1] = v0 * 1.25; continue; }

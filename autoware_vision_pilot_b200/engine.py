@@ -35,6 +35,11 @@ class _Stats(C.Structure):
                 ("shared_encoders", C.c_int), ("shared_trunks", C.c_int)]
 
 
+class _TapView(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("height", C.c_int), ("width", C.c_int), ("channels", C.c_int),
+                ("ld", C.c_int), ("pad", C.c_int), ("dtype", C.c_int)]
+
+
 _bound = False
 
 
@@ -63,6 +68,9 @@ def _bind():
                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.vp_engine_read_tap.restype = C.c_long
     lib.vp_engine_read_resized.argtypes = [C.c_void_p, C.c_void_p]
+    lib.vp_engine_tap_dev.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_TapView)]
+    lib.vp_engine_stream.argtypes = [C.c_void_p]
+    lib.vp_engine_stream.restype = C.c_void_p
     _bound = True
     return lib
 
@@ -96,17 +104,27 @@ class Engine:
     __del__ = close
 
     # ---- inference
-    def infer(self, frame: np.ndarray) -> None:
-        """frame: uint8 [h, w, 3] host array (C-contiguous rows)."""
-        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
+    @staticmethod
+    def _check_frame(frame: np.ndarray, allow_copy: bool) -> np.ndarray:
+        """uint8 [h, w, 3] with unit pixel strides (rows may be padded / an ROI: the row stride is passed on)."""
+        if not isinstance(frame, np.ndarray) or frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
             raise ValueError("frame must be uint8 [h, w, 3]")
-        if not frame.flags["C_CONTIGUOUS"]:
+        if frame.strides[2] != 1 or frame.strides[1] != 3 or frame.strides[0] < frame.shape[1] * 3:
+            if not allow_copy:
+                raise ValueError("submit() needs a frame with contiguous pixels (it is read asynchronously)")
             frame = np.ascontiguousarray(frame)
+        return frame
+
+    def infer(self, frame: np.ndarray) -> None:
+        """frame: uint8 [h, w, 3] host array (rows may be strided, e.g. an ROI view)."""
+        frame = self._check_frame(frame, allow_copy=True)
         h, w, _ = frame.shape
         L.check(self._lib.vp_engine_infer(self._h, frame.ctypes.data, h, w, frame.strides[0]), "vp_engine_infer")
 
     def submit(self, frame: np.ndarray) -> None:
-        """Asynchronous infer(): enqueue H2D + kernels + D2H, return at once; sync() completes it."""
+        """Asynchronous infer(): enqueue H2D + kernels + D2H, return at once; sync() completes it.
+        The caller keeps `frame` alive and unmodified until sync()."""
+        frame = self._check_frame(frame, allow_copy=False)
         h, w, _ = frame.shape
         L.check(self._lib.vp_engine_submit(self._h, frame.ctypes.data, h, w, frame.strides[0]), "vp_engine_submit")
 
@@ -172,6 +190,16 @@ class Engine:
         L.check(self._lib.vp_engine_time_kind(self._h, kind, reps, C.byref(ms), C.byref(fl), C.byref(n)),
                 "vp_engine_time_kind")
         return {"ms": ms.value, "flops": fl.value, "launches": n.value}
+
+    def tap_dev(self, name: str) -> dict:
+        """Device view of an intermediate tensor (NHWC 16-bit): {data, height, width, channels, ld, pad, dtype}."""
+        v = _TapView()
+        L.check(self._lib.vp_engine_tap_dev(self._h, name.encode(), C.byref(v)), "vp_engine_tap_dev")
+        return {k: getattr(v, k) for k, _ in _TapView._fields_}
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
 
     def read_resized(self) -> np.ndarray:
         buf = np.empty((320, 640, 3), dtype=np.uint8)

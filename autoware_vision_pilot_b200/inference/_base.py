@@ -25,9 +25,8 @@ def _resolve_checkpoint(path: str) -> str:
     out = os.path.splitext(path)[0] + ".vpw"
     try:
         return W.convert_checkpoint(path, out)
-    except PermissionError:
-        out = os.path.join(tempfile.gettempdir(), "vpb_" + str(abs(hash(os.path.abspath(path)))) + ".vpw")
-        return W.convert_checkpoint(path, out)
+    except (PermissionError, OSError):
+        return W.convert_checkpoint(path, W.cache_path_for(path))
 
 
 def _as_hwc_uint8(image) -> np.ndarray:
@@ -48,20 +47,24 @@ class NetworkInferBase:
 
     def __init__(self, checkpoint_path: str = "", *, resize_mode: str = "none", precision: str = "fp16",
                  gpu_id: int = 0):
-        if not checkpoint_path:
+        if not checkpoint_path and self.REQUIRE_CHECKPOINT:
             # scene_seg_infer.py:32-33 (message kept, typo included)
             raise ValueError("No path to checkpiont file provided in class initialization")
         self.device = f"cuda:{gpu_id}"
         print(f"Using {self.device} for inference")
         self._resize_mode = resize_mode
-        self._engine = E.Engine([self.KIND], [_resolve_checkpoint(checkpoint_path)], gpu_id=gpu_id,
+        vpw = _resolve_checkpoint(checkpoint_path) if checkpoint_path else self._vanilla_checkpoint()
+        self._engine = E.Engine([self.KIND], [vpw], gpu_id=gpu_id,
                                 dtype=precision, resize_mode=E.RESIZE_BY_NAME[resize_mode],
                                 convention=E.CONV_RGB, fetch_raw=True)
+
+    def _vanilla_checkpoint(self) -> str:
+        raise ValueError("No path to checkpiont file provided in class initialization")
 
     def _run(self, image) -> None:
         a = _as_hwc_uint8(image)
         h, w, _ = a.shape
-        if self._resize_mode == "none" and (w != 640 or h != 320):
+        if self.CHECK_SIZE and self._resize_mode == "none" and (w != 640 or h != 320):
             # scene_seg_infer.py:40-42
             raise ValueError("Incorrect input size - input image must have height of 320px and width of 640px")
         self._engine.infer(a)

@@ -124,6 +124,18 @@ int vp_engine_time_kind(vp_engine* e, int kind, int reps, float* ms, double* flo
  * ("<model_idx>/f0".."f4", "context", "neck", "pre") to host as fp32 NCHW. Returns element count. */
 long vp_engine_read_tap(vp_engine* e, const char* name, float* dst, long cap, int* c, int* h, int* w);
 
+/* Device view of an intermediate tensor (same names as vp_engine_read_tap): lets a host chain further
+ * device work on it without a copy — e.g. the multi-camera exchange of the EgoLanes "<idx>/fused"
+ * feature map (vp_b200_multicam.h).  NHWC 16-bit, `ld` elements per pixel, zero-bordered if pad. */
+typedef struct {
+  const void* data;
+  int height, width, channels, ld, pad;
+  int dtype;                        /* VPB_F16 | VPB_BF16 */
+} vp_tap_view;
+int vp_engine_tap_dev(vp_engine* e, const char* name, vp_tap_view* v);
+/* The cudaStream_t the engine enqueues on (the caller's, if one was passed in the config). */
+void* vp_engine_stream(vp_engine* e);
+
 /* The 640x320 uint8 image the fused pre-process produced for the last frame ([320][640][3], tensor
  * channel order) — lets the parity tests check the integer resize stage bit-exactly. */
 int vp_engine_read_resized(vp_engine* e, uint8_t* dst);

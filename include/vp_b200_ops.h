@@ -224,6 +224,10 @@ typedef struct {
   double pf_cte, pf_yaw_error, pf_curvature, pf_lane_width;
   double pf_cte_variance, pf_yaw_variance, pf_curv_variance, pf_lane_width_variance;
   int pf_fused_valid, pf_ran;
+  /* the 14-slot measurement vector (mean, variance) PathFinder::update built this frame
+   * (path_finder.cpp:97-157): what one camera contributes to the multi-camera fusion
+   * (vp_b200_multicam.h); all means NaN ("no measurement") when the BEV lines were not valid */
+  double pf_meas[14][2];
 } vpb_lateral_out;
 /* LaneFilter::reset + LaneTracker defaults */
 int vpb_lateral_init(vpb_lateral_state* state_dev, void* stream);
