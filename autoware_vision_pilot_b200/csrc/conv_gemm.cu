@@ -267,6 +267,56 @@ __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32
   }
 }
 
+// Staged form of epilogue_store_fast (tile kernel, ConvTranspose / 1x1 with plain store or GELU): the accumulator
+// row of a lane is ONE pixel, so direct stores are 32 separate 16-byte requests per instruction (a different 128-byte
+// line per lane) — profiles/r1_convt_timeline.md measured 4.5-6.7 k cycles per 128 x 256 tile for that, the L1 store
+// path's one-request-per-cycle limit, and it is what bounds the ConvTranspose layers (they write 4x the pixels they
+// read).  Here every 16-column chunk goes to shared memory in the 128-byte-swizzled box layout ([128 pixels][64 ch]
+// per slab: 4 wavefronts per warp store, the minimum) and one thread then issues a TMA store per 64-channel slab.
+template <class E, bool GELU>
+__device__ __forceinline__ void epilogue_to_smem(const ConvKParams& p, uint32_t t_row, const float* sbias, int part,
+                                                 uint32_t slab0, int row) {
+  const int nchunks = p.BN >> 4;
+  const uint32_t rbase = slab0 + static_cast<uint32_t>(row) * 128u;
+  const uint32_t rx = static_cast<uint32_t>(row & 7);
+  auto finish = [&](const uint32_t (&rr)[16], int chunk) {
+    const float4* sb = reinterpret_cast<const float4*>(sbias + chunk * 16);
+    float2 v[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = sb[i];
+      v[2 * i] = fadd2(make_float2(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1])), make_float2(b4.x, b4.y));
+      v[2 * i + 1] = fadd2(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(b4.z, b4.w));
+    }
+    if (GELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = act_gelu2(v[i]);
+    }
+    uint4 o0, o1;
+    o0.x = pack2<E>(v[0].x, v[0].y); o0.y = pack2<E>(v[1].x, v[1].y); o0.z = pack2<E>(v[2].x, v[2].y); o0.w = pack2<E>(v[3].x, v[3].y);
+    o1.x = pack2<E>(v[4].x, v[4].y); o1.y = pack2<E>(v[5].x, v[5].y); o1.z = pack2<E>(v[6].x, v[6].y); o1.w = pack2<E>(v[7].x, v[7].y);
+    const uint32_t slab = rbase + static_cast<uint32_t>(chunk >> 2) * (128u * 128u);
+    const uint32_t j = static_cast<uint32_t>(chunk & 3) * 2u;          // 16-byte piece index inside the 128-byte row
+    st_shared_v4(slab + ((j ^ rx) << 4), o0);
+    st_shared_v4(slab + (((j + 1u) ^ rx) << 4), o1);
+  };
+  int chunk = part;
+  for (; chunk + 4 < nchunks; chunk += 8) {
+    uint32_t ra[16], rb[16];
+    tmem_ld16(t_row + chunk * 16, ra);
+    tmem_ld16(t_row + (chunk + 4) * 16, rb);
+    tmem_ld_wait();
+    finish(ra, chunk);
+    finish(rb, chunk + 4);
+  }
+  if (chunk < nchunks) {
+    uint32_t ra[16];
+    tmem_ld16(t_row + chunk * 16, ra);
+    tmem_ld_wait();
+    finish(ra, chunk);
+  }
+}
+
 template <class E>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_row, int n0,
                                               const float* sbias, int part, const EpiPix& px) {
@@ -293,7 +343,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                  const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapA2,
-                 const __grid_constant__ CUtensorMap mapB2, const ConvKParams p) {
+                 const __grid_constant__ CUtensorMap mapB2,
+                 const __grid_constant__ CUtensorMap mapO, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
@@ -316,6 +367,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     if (p.kchunks2) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
+    if (p.tma_store) tma_prefetch_desc(&mapO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -475,6 +527,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
       if (p.trace && blockIdx.x == 0 && it < 16 && etid == 0) p.trace[it * 16 + 11] = clock64();
+      if (p.tma_store) {
+        // staged epilogue: accumulator -> swizzled shared-memory slabs -> one TMA store per 64-channel slab
+        const uint32_t slab0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;
+        const int h0 = thi * p.TH, w0 = twi * p.TW;
+        for (int q4 = 0; q4 < nb_tiles; ++q4) {
+          const int ph = ph0 + q4;
+          if (etid == 0) bulk_wait_read0();                 // the previous tile's stores have read the slabs
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + q4 * 128;
+          if (p.act == ACT_GELU) epilogue_to_smem<E, true>(p, t_row, s_bias[as], part, slab0, row);
+          else epilogue_to_smem<E, false>(p, t_row, s_bias[as], part, slab0, row);
+          fence_proxy_async();                              // generic-proxy smem writes -> visible to the TMA unit
+          if (q4 == nb_tiles - 1) tc_fence_before();
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          if (etid == 0) {
+            for (int sl = 0; sl < (p.BN >> 6); ++sl)
+              tma_store_5d(&mapO, slab0 + sl * (128 * 128), n0 + sl * 64, ph & 1, w0, ph >> 1, h0);
+            bulk_commit();
+          }
+        }
+        if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));    // accumulator drained (stores still in flight)
+        continue;
+      }
       for (int q4 = 0; q4 < nb_tiles; ++q4) {
         const int ph = ph0 + q4;
         const int oh = (p.phases > 1) ? 2 * h + (ph >> 1) : h;
@@ -495,6 +570,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
     }
   }
 
+  if (p.tma_store && threadIdx.x == 64) bulk_wait0();      // this thread issued the stores: all of them have completed
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -1225,6 +1301,15 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
+  if (a->bn <= 0 && a->phases == 4 && a->Cout > 64 && p.BN % 64) {
+    // ConvTranspose: N tiles made of whole 64-channel slabs (the TMA-store epilogue writes one box per slab)
+    int best = 256, best_waste = 1 << 30;
+    for (int bn = 256; bn >= 128; bn -= 64) {
+      const int waste = (a->Cout + bn - 1) / bn * bn - a->Cout;
+      if (waste < best_waste) { best_waste = waste; best = bn; }
+    }
+    p.BN = best;
+  }
   // split-K over a cluster for the smallest-M layers (context convs at 10x20: <= 32 tiles at BN = 128)
   p.splitk = 0;
   if (lin && a->mode != VPB_EPI_FINAL && a->dbg_splitk >= 0 && (a->bn <= 0 || a->dbg_splitk >= 2)) {
@@ -1352,9 +1437,15 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
                (p.tiles_h * p.tiles_w * p.tiles_n >= 2 * device_sm_count() || a->dbg_ms == 2)) ? 1 : 0;
     p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * (p.fuse4 ? 1 : p.phases);
     const size_t stage_bytes = kATileBytes + b_bytes * (p.fuse4 ? 4 : 1);
-    int stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes);
+    // staged TMA-store epilogue: plain store (ConvTranspose, with or without the fused skip link) or GELU, N tile made
+    // of whole 64-channel slabs; dbg_gb == 2 forces the direct-store epilogue (A/B comparison)
+    p.tma_store = (a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) && p.BN % 64 == 0 &&
+                   a->phases == 4 && a->dbg_gb != 2) ? 1 : 0;
+    const size_t slab_bytes = p.tma_store ? static_cast<size_t>(p.BN / 64) * 128 * 128 : 0;
+    int stages = static_cast<int>((kMaxDynSmem - 1024 - slab_bytes) / stage_bytes);
+    if (stages < 2 && p.tma_store) { p.tma_store = 0; stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes); }
     p.stages = std::max(2, std::min(stages, kMaxStages));
-    plan->smem_bytes = p.stages * stage_bytes + 1024;
+    plan->smem_bytes = p.stages * stage_bytes + (p.tma_store ? slab_bytes : 0) + 1024;
   }
   p.mg_tn = fast_div_magic(p.tiles_n); p.mg_tw = fast_div_magic(lin ? 1 : p.tiles_w);
   p.mg_tpp = fast_div_magic(lin ? 1 : p.tiles_n * p.tiles_h * p.tiles_w); p.mg_wp = fast_div_magic(p.WP);
@@ -1414,6 +1505,26 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   }
   plan->mapA2 = plan->mapA;
   plan->mapB2 = plan->mapB;
+  plan->mapO = plan->mapA;
+  if (p.tma_store) {
+    // output viewed as [h][a][w][b][c] (ConvTranspose phase (a,b) of pixel tile (h0,w0) is one tiled box)
+    const int s2 = a->phases == 4 ? 2 : 1;
+    const int pad = p.out_pad;
+    const size_t px = static_cast<size_t>(a->ldo) * 2;
+    const size_t pitch = static_cast<size_t>(a->W * s2 + 2 * pad) * px;
+    uint8_t* base = static_cast<uint8_t*>(a->out) + pad * pitch + pad * px;
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(a->ldo), static_cast<cuuint64_t>(s2), static_cast<cuuint64_t>(a->W),
+                          static_cast<cuuint64_t>(s2), static_cast<cuuint64_t>(a->H)};
+    cuuint64_t strides[4] = {px, px * s2, pitch, pitch * s2};
+    cuuint32_t box[5] = {64, 1, static_cast<cuuint32_t>(p.TW), 1, static_cast<cuuint32_t>(p.TH)};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    r = enc(&plan->mapO, dt, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      vpb_set_error("conv: cuTensorMapEncodeTiled(O) failed: %d", static_cast<int>(r));
+      return VPB_ERR_CUDA;
+    }
+  }
   if (a->in2) {
     // second input at output resolution, viewed as [h][a][w][b][c] (s = 2 for a ConvTranspose,
     // a = b = 0 and s = 1 otherwise); box = one pixel tile of one phase
@@ -1478,8 +1589,8 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     if (bf) VPB_CUDA_OK(launch_k(conv3x3_lin_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
     else VPB_CUDA_OK(launch_k(conv3x3_lin_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
   } else {
-    if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->mapA2, plan->mapB2, plan->p));
-    else VPB_CUDA_OK(launch_k(conv_gemm_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->mapA2, plan->mapB2, plan->p));
+    if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->mapA2, plan->mapB2, plan->mapO, plan->p));
+    else VPB_CUDA_OK(launch_k(conv_gemm_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->mapA2, plan->mapB2, plan->mapO, plan->p));
   }
   return VPB_OK;
 }

@@ -20,6 +20,7 @@ struct ConvKParams {
   int stages;                    // smem pipeline depth (tile kernel)
   int lin;                       // 1 = linear-padded 3x3 kernel
   int fuse4;                     // tile kernel, ConvTranspose: all 4 phases per CTA tile
+  int tma_store;                 // tile kernel: epilogue stages the tile in shared memory and writes it with TMA stores
   int na, nb;                    // linear kernel: activation-segment / weight-slot ring depths
   int gb;                        // linear kernel: weight tiles per slot (3 = one kernel row per barrier)
   int ms;                        // linear kernel: M sub-tiles (of 128 pixels) per CTA tile, 1, 2 or 4
@@ -43,6 +44,7 @@ struct ConvKParams {
 struct ConvPlan {
   CUtensorMap mapA, mapB;
   CUtensorMap mapA2, mapB2;      // second 1x1 input and its weights (copies of mapA/mapB when unused)
+  CUtensorMap mapO;              // output view [h][a][w][b][c] for the TMA-store epilogue (copy of mapA when unused)
   ConvKParams p;
   int dtype;
   int grid;

@@ -104,6 +104,8 @@ struct OpRec {
   std::string name;
   std::function<int(cudaStream_t)> launch;
   double flops = 0;
+  double bytes = 0;     // algorithmic HBM bytes per launch (HBM-bound stages; SURVEY.md 8d definitions)
+  std::string kname;    // kernel the op launches (roofline report groups launches by kernel)
   bool gemm = false;
   int kind = 0;   // 0 = not a convolution GEMM, 1 = conv_gemm_kernel, 2 = conv3x3_lin_kernel, 3 = conv3x3_pair_kernel
   int lane = 0;   // execution lane (= index of the model that owns the op); lanes run concurrently
@@ -265,12 +267,14 @@ struct vp_engine {
     plans.push_back(std::move(plan));
     OpRec op; op.name = name; op.flops = pp->flops; op.gemm = true; op.lane = cur_lane;
     op.kind = pp->p.lin ? (pp->p.pair ? 3 : 2) : 1;
+    op.kname = !pp->p.lin ? "conv_gemm_kernel" : pp->p.splitk ? "conv3x3_splitk_kernel" : pp->p.pair ? "conv3x3_pair_kernel" : "conv3x3_lin_kernel";
     op.launch = [pp](cudaStream_t s) { return conv_plan_launch(pp, s); };
     ops.push_back(std::move(op));
     return VPB_OK;
   }
-  void add_op(const std::string& name, std::function<int(cudaStream_t)> fn, double flops = 0) {
-    OpRec op; op.name = name; op.launch = std::move(fn); op.flops = flops; op.lane = cur_lane;
+  void add_op(const std::string& name, const char* kname, std::function<int(cudaStream_t)> fn, double flops = 0,
+              double bytes = 0) {
+    OpRec op; op.name = name; op.kname = kname; op.launch = std::move(fn); op.flops = flops; op.bytes = bytes; op.lane = cur_lane;
     ops.push_back(std::move(op));
   }
 };
@@ -360,8 +364,8 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
   Tens x = e.act_alloc(kNetH / 2, kNetW / 2, 32);
   {
     const void* in = e.d_pre; void* o = x.p;
-    e.add_op(tag + "stem", [=](cudaStream_t st) { return vpb_stem_conv(dt, in, kNetH, kNetW, d_stem, d_stem_b, o, st); },
-             2.0 * x.H * x.W * 32 * 27);
+    e.add_op(tag + "stem", "stem_conv_kernel", [=](cudaStream_t st) { return vpb_stem_conv(dt, in, kNetH, kNetW, d_stem, d_stem_b, o, st); },
+             2.0 * x.H * x.W * 32 * 27, 2.0 * kNetH * kNetW * 4 + 2.0 * x.H * x.W * 32);
   }
   Tens stage_out[9];
   stage_out[0] = x;
@@ -397,8 +401,8 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
       long long* d_part = e.gap_alloc(ce);
       {
         const void* in = cur.p; void* o = dwo.p; const int H = cur.H, W = cur.W;
-        e.add_op(nm + "dw", [=](cudaStream_t st) { return vpb_depthwise(dt, in, H, W, ce, k, s_, d_dw, d_dwb, o, d_part, st); },
-                 2.0 * g.Ho * g.Wo * ce * k * k);
+        e.add_op(nm + "dw", "depthwise_kernel", [=](cudaStream_t st) { return vpb_depthwise(dt, in, H, W, ce, k, s_, d_dw, d_dwb, o, d_part, st); },
+                 2.0 * g.Ho * g.Wo * ce * k * k, 2.0 * H * W * ce + 2.0 * g.Ho * g.Wo * ce);
       }
       // SE gate folded into the projection weights
       const std::string sp = bp + std::to_string(bi + 1) + ".";
@@ -419,9 +423,9 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
       void* d_wscaled = e.dalloc(static_cast<size_t>(cout) * ce * 2, false);
       {
         const int HW = g.Ho * g.Wo;
-        e.add_op(nm + "se", [=](cudaStream_t st) {
+        e.add_op(nm + "se", "se_scale_kernel", [=](cudaStream_t st) {
           return vpb_se_scale(dt, d_part, HW, ce, sq, d_f1, d_b1, d_f2, d_b2, d_proj, cout, d_wscaled, nullptr, st);
-        }, 2.0 * (2.0 * ce * sq));
+        }, 2.0 * (2.0 * ce * sq), 8.0 * ce * kGapReplicas + 8.0 * ce * sq + 4.0 * cout * ce + 2.0 * cout * ce);
       }
       // 1x1 project + BN (+ residual; StochasticDepth is identity in eval)
       const bool residual = (s_ == 1 && ci == cout);
@@ -495,7 +499,7 @@ static int build_context(vp_engine& e, const WeightMap& w, const std::string& p,
   float* d_v = static_cast<float*>(e.dalloc(C * 4, false));
   {
     const void* in = feat.p;
-    e.add_op(tag + "gap", [=](cudaStream_t st) { return vpb_gap(dt, in, HW, C, C, d_v, st); });
+    e.add_op(tag + "gap", "gap_kernel", [=](cudaStream_t st) { return vpb_gap(dt, in, HW, C, C, d_v, st); }, 0.0, 2.0 * HW * C);
   }
   const int dims[4] = {C, 800, 800, 200};
   const int acts[3] = {ACT_GELU, ACT_GELU, ACT_SIGMOID};
@@ -508,8 +512,8 @@ static int build_context(vp_engine& e, const WeightMap& w, const std::string& p,
     float* y = static_cast<float*>(e.dalloc(dims[i + 1] * 4, false));
     const int in_f = dims[i], out_f = dims[i + 1], a = acts[i];
     const float* xin = cur;
-    e.add_op(tag + "mlp" + std::to_string(i), [=](cudaStream_t st) { return vpb_linear(xin, dw_, db, in_f, out_f, a, y, st); },
-             2.0 * in_f * out_f);
+    e.add_op(tag + "mlp" + std::to_string(i), "linear_kernel", [=](cudaStream_t st) { return vpb_linear(xin, dw_, db, in_f, out_f, a, y, st); },
+             2.0 * in_f * out_f, 4.0 * in_f * out_f);
     cur = y;
   }
   const HostTensor *w3 = find_w_shaped(w, p + "context_layer_3.weight", {128, 1, 3, 3}), *b3 = find_w_shaped(w, p + "context_layer_3.bias", {128});
@@ -518,8 +522,8 @@ static int build_context(vp_engine& e, const WeightMap& w, const std::string& p,
   Tens c4 = e.act_alloc(feat.H, feat.W, 128, /*pad=*/1);
   {
     const float* xin = cur; void* o = c4.p; const int H = feat.H, W = feat.W;
-    e.add_op(tag + "ctx3", [=](cudaStream_t st) { return vpb_ctx_conv1(dt, xin, H, W, d_w3, d_b3, 128, o, 1, st); },
-             2.0 * HW * 128 * 9);
+    e.add_op(tag + "ctx3", "ctx_conv1_kernel", [=](cudaStream_t st) { return vpb_ctx_conv1(dt, xin, H, W, d_w3, d_b3, 128, o, 1, st); },
+             2.0 * HW * 128 * 9, 2.0 * (H + 2) * (W + 2) * 128);
   }
   Tens c5, c6;
   int rc = conv_layer(e, w, p + "context_layer_4", tag + "ctx4", c4, 9, ACT_GELU, VPB_EPI_STORE, &c5, nullptr);
@@ -621,7 +625,8 @@ static int build_model(vp_engine& e, int idx, int kind, const WeightMap& w) {
       feat = e.act_alloc(enc.f[4].H, enc.f[4].W, 1456);
       const int dt = e.dtype; const void *f0 = enc.f[0].p, *f1 = enc.f[1].p, *f2 = enc.f[2].p, *f3 = enc.f[3].p, *f4 = enc.f[4].p;
       void* o = feat.p; const int H4 = feat.H, W4 = feat.W;
-      e.add_op(tag + "fuse", [=](cudaStream_t st) { return vpb_fuse_pool_concat(dt, f0, f1, f2, f3, f4, H4, W4, o, st); });
+      e.add_op(tag + "fuse", "fuse_pool_kernel", [=](cudaStream_t st) { return vpb_fuse_pool_concat(dt, f0, f1, f2, f3, f4, H4, W4, o, st); },
+               0.0, 2.0 * (160.0 * 320 * 32 + 80.0 * 160 * 24 + 40.0 * 80 * 40 + 20.0 * 40 * 80 + 200.0 * 1280 + 200.0 * 1456));
       e.taps[tag + "fused"] = feat;
     }
     Tens ctx;
@@ -1021,3 +1026,55 @@ extern "C" int vp_engine_tap_dev(vp_engine* e, const char* name, vp_tap_view* v)
 }
 
 extern "C" void* vp_engine_stream(vp_engine* e) { return e ? static_cast<void*>(e->stream) : nullptr; }
+
+// ---------------------------------------------------------------- per-kernel timing for the roofline report
+extern "C" int vp_engine_kernel_names(vp_engine* e, const char** names, int cap, int* n) {
+  if (!e || !n) return VPB_ERR_ARG;
+  static const char* kPreName = "preprocess";
+  std::vector<const char*> v{kPreName};
+  for (const auto& op : e->ops) {
+    bool seen = false;
+    for (const char* x : v) if (op.kname == x) { seen = true; break; }
+    if (!seen) v.push_back(op.kname.c_str());
+  }
+  *n = static_cast<int>(v.size());
+  if (names) for (int i = 0; i < *n && i < cap; ++i) names[i] = v[i];
+  return VPB_OK;
+}
+
+extern "C" int vp_engine_time_kernel(vp_engine* e, const char* kname, int reps, float* ms, double* flops,
+                                     double* bytes, int* launches) {
+  if (!e || !kname || !ms || reps <= 0) return VPB_ERR_ARG;
+  if (!e->g_src) { vpb_set_error("vp_engine_time_kernel: run one inference first"); return VPB_ERR_STATE; }
+  DeviceGuard guard(e->gpu_id);
+  const bool is_pre = strcmp(kname, "preprocess") == 0;
+  cudaEvent_t a, b;
+  VPB_CUDA_OK(cudaEventCreate(&a));
+  VPB_CUDA_OK(cudaEventCreate(&b));
+  double fl = 0.0, by = 0.0;
+  int n = 0;
+  for (int r = -1; r < reps; ++r) {            // r = -1: untimed warm-up pass
+    if (r == 0) VPB_CUDA_OK(cudaEventRecord(a, e->stream));
+    if (is_pre) {
+      const int rc = e->pre.launch(e->g_src, e->g_stride, e->cfg.convention, e->dtype, e->d_pre, e->d_resized, e->stream);
+      if (rc) return rc;
+      // frame read + 3 x 320 x 640 16-bit tensor written
+      if (r >= 0) { by += 3.0 * e->g_h * e->g_w + 2.0 * 3 * kNetH * kNetW; ++n; }
+      continue;
+    }
+    for (auto& op : e->ops) {
+      if (op.kname != kname) continue;
+      const int rc = op.launch(e->stream);
+      if (rc) return rc;
+      if (r >= 0) { fl += op.flops; by += op.bytes; ++n; }
+    }
+  }
+  VPB_CUDA_OK(cudaEventRecord(b, e->stream));
+  VPB_CUDA_OK(cudaStreamSynchronize(e->stream));
+  VPB_CUDA_OK(cudaEventElapsedTime(ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  if (flops) *flops = fl;
+  if (bytes) *bytes = by;
+  if (launches) *launches = n;
+  return VPB_OK;
+}

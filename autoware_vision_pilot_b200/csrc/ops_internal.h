@@ -20,6 +20,8 @@ struct PreprocessPlan {
   int OH = kNetH, OW = kNetW;
   int xks = 0, yks = 0;
   int rows_cap = 0, patch_w_cap = 0;
+  int TY = 20, pitch = 0, xt = 16;   // Pillow kernel: output rows per block, smem row pitch (bytes), tap capacity (16 | 32)
+  int device = -1;                   // device that owns d_tables
   size_t smem_bytes = 0;
   int* d_tables = nullptr;
   size_t off_xb = 0, off_xk = 0, off_yb = 0, off_yk = 0;

@@ -191,6 +191,22 @@ class Engine:
                 "vp_engine_time_kind")
         return {"ms": ms.value, "flops": fl.value, "launches": n.value}
 
+    def kernel_names(self) -> List[str]:
+        n = C.c_int()
+        names = (C.c_char_p * 64)()
+        self._lib.vp_engine_kernel_names.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_int)]
+        L.check(self._lib.vp_engine_kernel_names(self._h, names, 64, C.byref(n)), "vp_engine_kernel_names")
+        return [names[i].decode() for i in range(min(n.value, 64))]
+
+    def time_kernel_name(self, kname: str, reps: int = 10) -> dict:
+        """All launches of kernel `kname` of one frame, back to back `reps` times between one CUDA-event pair."""
+        ms, fl, by, n = C.c_float(), C.c_double(), C.c_double(), C.c_int()
+        self._lib.vp_engine_time_kernel.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_float),
+                                                    C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.check(self._lib.vp_engine_time_kernel(self._h, kname.encode(), reps, C.byref(ms), C.byref(fl), C.byref(by),
+                                                C.byref(n)), "vp_engine_time_kernel")
+        return {"ms": ms.value, "flops": fl.value, "bytes": by.value, "launches": n.value}
+
     def tap_dev(self, name: str) -> dict:
         """Device view of an intermediate tensor (NHWC 16-bit): {data, height, width, channels, ld, pad, dtype}."""
         v = _TapView()

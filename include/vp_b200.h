@@ -120,6 +120,16 @@ int vp_engine_profile(vp_engine* e, int max_ops, float* ms, double* flops, const
  * duration of the dominant kernel" bench.py's roofline uses; the operands of the ~30 layers cycle through
  * more memory than L2 holds. */
 int vp_engine_time_kind(vp_engine* e, int kind, int reps, float* ms, double* flops, int* launches);
+/* Per-kernel form of the above for the roofline report: the distinct kernel names of the frame
+ * ("preprocess", "stem_conv_kernel", "depthwise_kernel", "se_scale_kernel", "conv3x3_pair_kernel", ...), and
+ * all launches of one of them issued back to back `reps` times between ONE CUDA-event pair (after an untimed
+ * pass).  flops = algorithmic 2*MAC, bytes = algorithmic HBM bytes (SURVEY.md 8d definitions: tensors in +
+ * out of the stage) of the timed launches.  A large `reps` (seconds of device time) makes it a sustained
+ * measurement. */
+int vp_engine_kernel_names(vp_engine* e, const char** names, int cap, int* n);
+int vp_engine_time_kernel(vp_engine* e, const char* kname, int reps, float* ms, double* flops, double* bytes,
+                          int* launches);
+
 /* Intermediate activations for the per-tap parity tests: copies tensor `name`
  * ("<model_idx>/f0".."f4", "context", "neck", "pre") to host as fp32 NCHW. Returns element count. */
 long vp_engine_read_tap(vp_engine* e, const char* name, float* dst, long cap, int* c, int* h, int* w);

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for h in ("vp_b200.h", "vp_b200_ops.h"):
+    for h in ("vp_b200.h", "vp_b200_ops.h", "vp_b200_multicam.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(vpb?_[a-z0-9_]+)\s*\(", src))
@@ -93,9 +93,46 @@ def test_vpw_writer_layout(tmp_path):
 def test_infer_helpers_keep_reference_error_behaviour():
     from autoware_vision_pilot_b200.inference import (DomainSegNetworkInfer, EgoLanesNetworkInfer,
                                                       Scene3DNetworkInfer, SceneSegNetworkInfer)
-    for K in (SceneSegNetworkInfer, Scene3DNetworkInfer, DomainSegNetworkInfer, EgoLanesNetworkInfer):
+    for K in (SceneSegNetworkInfer, Scene3DNetworkInfer, DomainSegNetworkInfer):
         with pytest.raises(ValueError):
             K(checkpoint_path="")          # scene_seg_infer.py:32-33
+    # EgoLanes accepts an empty path ("vanilla" randomly initialised model, ego_lanes_infer.py:34-44): no ValueError;
+    # without a GPU the engine itself then refuses (no CPU fallback)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            EgoLanesNetworkInfer(checkpoint_path="")
+
+
+def test_vanilla_ego_lanes_state_dict_has_the_reference_layout():
+    """Names / shapes of the randomly initialised EgoLanes checkpoint == the oracle's state_dict spec (which is
+    strict-loaded into the unmodified reference module in tests/test_oracle_vs_reference.py)."""
+    from oracle import synth
+    a = [(n, tuple(s)) for n, s in W.ego_lanes_spec()]
+    b = [(n, tuple(s)) for n, s, _ in synth.state_dict_spec("ego_lanes")]
+    assert a == b
+    sd = W.vanilla_ego_lanes_state_dict()
+    assert sd["BEVBackbone.encoder.0.1.running_var"].min() == 1.0 and not sd["BEVBackbone.encoder.0.1.bias"].any()
+    w = sd["EgopathNeck.decode_layer_0.weight"]
+    assert abs(w).max() <= 1.0 / np.sqrt(1456 * 9) and w.std() > 0
+
+
+def test_write_vpw_is_atomic_under_concurrent_writers(tmp_path):
+    """Several ranks converting the same checkpoint at start-up must never publish a partial file."""
+    import multiprocessing as mp
+    sd = {"a.weight": np.arange(1 << 16, dtype=np.float32)}
+    path = str(tmp_path / "shared.vpw")
+    ctx = mp.get_context("fork")
+    procs = [ctx.Process(target=W.write_vpw, args=(sd, path)) for _ in range(6)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join()
+        assert p.exitcode == 0
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"VPW1" and len(raw) == 4 + 4 + 4 + 8 + 8 + 4 + 8 + 4 * (1 << 16)
+    assert not [f for f in os.listdir(tmp_path) if f.endswith(".tmp")]
+    assert W.cache_path_for("/x/y.pth") == W.cache_path_for("/x/y.pth")          # stable across calls / processes
 
 
 def test_engine_create_fails_loudly_without_gpu(tmp_path):
@@ -114,7 +151,10 @@ def test_ctypes_mirrors_match_the_c_struct_layouts(tmp_path):
     equal what ctypes computes — catches a field added on one side only."""
     import subprocess
     from autoware_vision_pilot_b200 import engine as E
+    from autoware_vision_pilot_b200 import multicam as M
     mirrors = {
+        "vp_tap_view": (E._TapView, {}),
+        "vp_multicam_view": (M._View, {}),
         "vpb_conv_args": (L.ConvArgs, {"inp": "in"}),
         "vpb_lateral_state": (L.LateralState, {}),
         "vpb_lateral_out": (L.LateralOut, {}),
@@ -122,7 +162,7 @@ def test_ctypes_mirrors_match_the_c_struct_layouts(tmp_path):
         "vp_output": (E._Output, {}),
         "vp_engine_stats": (E._Stats, {}),
     }
-    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vp_b200.h"', '#include "vp_b200_ops.h"',
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vp_b200.h"', '#include "vp_b200_ops.h"', '#include "vp_b200_multicam.h"',
              'int main(void) {']
     for cname, (cls, rename) in mirrors.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

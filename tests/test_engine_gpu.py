@@ -98,9 +98,34 @@ def test_single_model_parity_via_infer_helpers(model, ckpt, frame0, tmp_path):
         masks, ids = net.ego_lanes_masks(ref)
         bad = helper._engine.cls(0) != ids
         assert not (bad & (np.abs(ref).min(axis=0) > tau)).any()
-    # reference error behaviour at the boundary (scene_seg_infer.py:40-42)
-    with pytest.raises(ValueError):
+    # reference error behaviour at the boundary: the three segmentation/depth helpers check the size and raise
+    # ValueError (scene_seg_infer.py:40-42); EgoLanes has no check, its network fails inside torch with a RuntimeError
+    # at the context block's reshape([10, 20]) (ego_lanes_infer.py:51-62, auto_steer_context.py:44)
+    with pytest.raises(RuntimeError if model == "ego_lanes" else ValueError):
         helper.inference(Image.fromarray(np.zeros((100, 100, 3), np.uint8)))
+    if model == "ego_lanes":
+        got2 = helper.inference(small)                               # HWC uint8 ndarray is accepted like a PIL image
+        assert np.array_equal(got2, got)
+
+
+def test_ego_lanes_vanilla_model_and_pth_checkpoint(ckpt, frame0, tmp_path):
+    """(1) EgoLanesNetworkInfer("") runs the randomly initialised network like the reference (ego_lanes_infer.py:34-44);
+    (2) a reference-format .pth (torch.save(state_dict)) goes through convert_checkpoint into every helper
+    (scene_seg_infer.py:30-31) and gives the same result as the .vpw written directly."""
+    from PIL import Image
+    from autoware_vision_pilot_b200 import inference as I
+    _, small = frame0
+    v = I.EgoLanesNetworkInfer(checkpoint_path="")
+    out = v.inference(Image.fromarray(small))
+    assert out.shape == (3, 80, 160) and out.dtype == np.float32 and np.isfinite(out).all()
+    for model, cls in (("scene_seg", I.SceneSegNetworkInfer), ("ego_lanes", I.EgoLanesNetworkInfer)):
+        sd, vpw = ckpt[model]
+        pth = str(tmp_path / f"{model}.pth")
+        torch.save({k: (t if torch.is_tensor(t) else torch.as_tensor(t)) for k, t in sd.items()}, pth)
+        a = cls(checkpoint_path=pth).inference(Image.fromarray(small))
+        b = cls(checkpoint_path=vpw).inference(Image.fromarray(small))
+        assert np.array_equal(a, b)
+        assert os.path.exists(os.path.splitext(pth)[0] + ".vpw")
 
 
 def test_scene_seg_taps_and_golden(ckpt, frame0):
