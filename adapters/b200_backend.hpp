@@ -40,7 +40,12 @@ public:
   {
     vp_engine_config cfg{};
     cfg.gpu_id = gpu_id;
-    cfg.dtype = (precision == "bf16") ? VPB_BF16 : VPB_F16;   // "fp16" (reference default) and "fp32" map to fp16 operands / fp32 accumulate
+    // "fp16" (reference default) / "bf16": 16-bit operands, fp32 accumulate; "fp32" (tensorrt_backend.cpp:129-131 builds
+    // an FP32 engine): the split-fp16 fp32-grade mode; anything else is rejected like an unknown TensorRT precision
+    if (precision != "fp16" && precision != "bf16" && precision != "fp32")
+      throw std::runtime_error("B200Backend: unsupported precision '" + precision + "' (fp16 | bf16 | fp32)");
+    cfg.dtype = (precision == "bf16") ? VPB_BF16 : VPB_F16;
+    cfg.precision = (precision == "fp32") ? VP_PREC_SPLIT : VP_PREC_16;
     cfg.resize_mode = VPB_RESIZE_CV_LINEAR;
     cfg.convention = VPB_CONV_BGR_NOSWAP;
     cfg.n_models = 1;

@@ -33,7 +33,10 @@ public:
   {
     vp_engine_config cfg{};
     cfg.gpu_id = device_id;
+    if (precision != "fp16" && precision != "bf16" && precision != "fp32")
+      throw std::runtime_error("EgoLanesB200Engine: unsupported precision '" + precision + "' (fp16 | bf16 | fp32)");
     cfg.dtype = (precision == "bf16") ? VPB_BF16 : VPB_F16;
+    cfg.precision = (precision == "fp32") ? VP_PREC_SPLIT : VP_PREC_16;   // fp32 engines: split-fp16 fp32-grade mode
     cfg.resize_mode = VPB_RESIZE_CV_LINEAR;
     cfg.convention = VPB_CONV_BGR_SWAP;
     cfg.n_models = 1;

@@ -45,6 +45,17 @@ template <class E> __device__ __forceinline__ typename E::T from_f32(float v);
 template <> __device__ __forceinline__ __half from_f32<F16>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<BF16>(float v) { return __float2bfloat16_rn(v); }
 
+// Split-fp16 ("fp32-grade") storage: x = hi + lo with hi = round16(x), lo = round16(x - hi) (~22 significant bits).
+template <class E> __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack2<E>(a, b);
+  const float2 h = unpack2<E>(hi);
+  lo = pack2<E>(a - h.x, b - h.y);
+}
+template <class E> __device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
+  const float2 h = unpack2<E>(hi), l = unpack2<E>(lo);
+  return make_float2(h.x + l.x, h.y + l.y);
+}
+
 // ----------------------------------------------------------------------------
 // Activations (reference: nn.GELU() exact-erf, scene_neck.py:8; SiLU/sigmoid in
 // torchvision EfficientNet-B0).

@@ -95,6 +95,8 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
   const int nchunks = p.BN >> 4;
   typename E::T* out = reinterpret_cast<typename E::T*>(p.out);
   const typename E::T* res = reinterpret_cast<const typename E::T*>(p.res);
+  typename E::T* out_lo = reinterpret_cast<typename E::T*>(p.out_lo);                // split-fp16 mode only
+  const typename E::T* res_lo = reinterpret_cast<const typename E::T*>(p.res_lo);
   for (int chunk0 = part; chunk0 < nchunks; chunk0 += 4 * NC) {
     uint32_t rr[NC][16];
 #pragma unroll
@@ -168,15 +170,25 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
             rv[c][j] = rok[c][j] ? *reinterpret_cast<const uint4*>(rp + 8 * j) : make_uint4(0, 0, 0, 0);
           }
         }
+        uint4 rl[NC][2];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            rl[c][j] = (p.split && rok[c][j])
+                           ? *reinterpret_cast<const uint4*>(res_lo + (px.roff + n0 + (chunk0 + 4 * c) * 16) + 8 * j)
+                           : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int c = 0; c < NC; ++c)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (!rok[c][j]) continue;
             const uint32_t rw[4] = {rv[c][j].x, rv[c][j].y, rv[c][j].z, rv[c][j].w};
+            const uint32_t rwl[4] = {rl[c][j].x, rl[c][j].y, rl[c][j].z, rl[c][j].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float2 f = unpack2<E>(rw[i]);
+              float2 f = unpack2<E>(rw[i]);
+              if (p.split) { const float2 fl = unpack2<E>(rwl[i]); f.x += fl.x; f.y += fl.y; }
               float& a = v[c][8 * j + 2 * i];
               float& b = v[c][8 * j + 2 * i + 1];
               if (p.mode == VPB_EPI_ADD) { a += f.x; b += f.y; }
@@ -197,6 +209,16 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
             o.z = pack2<E>(v[c][8 * j + 4], v[c][8 * j + 5]);
             o.w = pack2<E>(v[c][8 * j + 6], v[c][8 * j + 7]);
             *reinterpret_cast<uint4*>(op + 8 * j) = o;
+            if (p.split) {          // low half: what the 16-bit rounding of the high half lost
+              const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+              uint32_t lw[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 h = unpack2<E>(ow[i]);
+                lw[i] = pack2<E>(v[c][8 * j + 2 * i] - h.x, v[c][8 * j + 2 * i + 1] - h.y);
+              }
+              *reinterpret_cast<uint4*>(out_lo + (px.ooff + n) + 8 * j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
           }
         }
       }
@@ -322,8 +344,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_r
                                               const float* sbias, int part, const EpiPix& px) {
   // NC = 2 (two chunks per iteration) measured 2-3 % slower and makes ptxas spill in every kernel that
   // contains it (96-register cap), so only the one-chunk form is instantiated.
-  if (p.mode == VPB_EPI_STORE && n0 + p.BN <= p.ldo && p.act == ACT_GELU) epilogue_store_fast<E, true>(p, t_row, n0, sbias, part, px);
-  else if (p.mode == VPB_EPI_STORE && n0 + p.BN <= p.ldo && p.act == ACT_NONE) epilogue_store_fast<E, false>(p, t_row, n0, sbias, part, px);
+  if (!p.split && p.mode == VPB_EPI_STORE && n0 + p.BN <= p.ldo && p.act == ACT_GELU) epilogue_store_fast<E, true>(p, t_row, n0, sbias, part, px);
+  else if (!p.split && p.mode == VPB_EPI_STORE && n0 + p.BN <= p.ldo && p.act == ACT_NONE) epilogue_store_fast<E, false>(p, t_row, n0, sbias, part, px);
   else epilogue_chunks<E, 1>(p, t_row, n0, sbias, part, px);
 }
 
@@ -340,11 +362,12 @@ __device__ __forceinline__ void stage_bias(const ConvKParams& p, float* dst, int
 // ------------------------------------------------------------------------------------------------
 template <class E>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
-                 const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ CUtensorMap mapA2,
-                 const __grid_constant__ CUtensorMap mapB2,
-                 const __grid_constant__ CUtensorMap mapO, const ConvKParams p) {
+conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
+  const CUtensorMap& mapA = maps.A;
+  const CUtensorMap& mapB = maps.B;
+  const CUtensorMap& mapA2 = maps.A2;
+  const CUtensorMap& mapB2 = maps.B2;
+  const CUtensorMap& mapO = maps.O;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
@@ -368,6 +391,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
     tma_prefetch_desc(&mapB);
     if (p.kchunks2) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
     if (p.tma_store) tma_prefetch_desc(&mapO);
+    if (p.split) { tma_prefetch_desc(&maps.Alo); tma_prefetch_desc(&maps.Blo); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -392,8 +416,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
   pdl_wait();                // predecessor's outputs (our inputs) are complete and visible from here on
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[255] = clock64();
 
+  // split-fp16 mode: every K chunk is walked three times (A_hi W_hi, A_lo W_hi, A_hi W_lo) into the same accumulator
+  const int nseg = p.split ? 3 : 1;
   const int kiters = p.taps * p.kchunks;
-  const int kiters_all = kiters + p.kchunks2;   // + the fused skip link's K chunks
+  const int kiters_all = (kiters + p.kchunks2) * nseg;   // + the fused skip link's K chunks
   const int tiles_per_phase = p.tiles_n * p.tiles_h * p.tiles_w;
 
   if (warp == 0) {
@@ -416,42 +442,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
         const int dx = (p.taps == 9) ? (t % 3 - 1) : 0;
         const int wsel = (p.phases > 1) ? ph : t;
         for (int c = 0; c < p.kchunks; ++c) {
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-          if (elect_one()) {
-            const uint32_t full = smem_u32(&bar_full[stage]);
-            const uint32_t sa = smem_base + stage * stage_bytes;
-            if (p.trace && blockIdx.x == 0) {
-              const int ti = (tile - blockIdx.x) / gridDim.x, k = t * p.kchunks + c;
-              if (ti < 16 && k < 4) p.trace[ti * 16 + k] = clock64();
-            }
-            mbar_arrive_expect_tx(full, stage_bytes);
-            tma_load_4d(sa, &mapA, full, c * 64, w0 + dx, h0 + dy, 0);
-            if (p.fuse4) {
+          for (int seg = 0; seg < nseg; ++seg) {
+            const CUtensorMap* mA = seg == 1 ? &maps.Alo : &mapA;
+            const CUtensorMap* mB = seg == 2 ? &maps.Blo : &mapB;
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            if (elect_one()) {
+              const uint32_t full = smem_u32(&bar_full[stage]);
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              if (p.trace && blockIdx.x == 0) {
+                const int ti = (tile - blockIdx.x) / gridDim.x, k = t * p.kchunks + c;
+                if (ti < 16 && k < 4) p.trace[ti * 16 + k] = clock64();
+              }
+              mbar_arrive_expect_tx(full, stage_bytes);
+              tma_load_4d(sa, mA, full, c * 64, w0 + dx, h0 + dy, 0);
+              if (p.fuse4) {
 #pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4)
-                tma_load_3d(sa + kATileBytes + q4 * b_tile_bytes, &mapB, full, c * 64, n0, q4);
-            } else {
-              tma_load_3d(sa + kATileBytes, &mapB, full, c * 64, n0, wsel);
+                for (int q4 = 0; q4 < 4; ++q4)
+                  tma_load_3d(sa + kATileBytes + q4 * b_tile_bytes, mB, full, c * 64, n0, q4);
+              } else {
+                tma_load_3d(sa + kATileBytes, mB, full, c * 64, n0, wsel);
+              }
             }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
       // fused skip link: the same output pixels seen in the second input (at output resolution);
       // for a ConvTranspose phase (a,b) that is the pixel set (2h+a, 2w+b), addressed through a
       // 5-D view [h][a][w][b][c] of the tensor so a plain tiled box picks every second pixel
       for (int c2 = 0; c2 < p.kchunks2; ++c2) {
-        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-        if (elect_one()) {
-          const uint32_t full = smem_u32(&bar_full[stage]);
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          mbar_arrive_expect_tx(full, stage_bytes);
-          tma_load_5d(sa, &mapA2, full, c2 * 64, ph & 1, w0, ph >> 1, h0);
-          tma_load_3d(sa + kATileBytes, &mapB2, full, c2 * 64, n0, 0);
+        for (int seg = 0; seg < nseg; ++seg) {
+          const CUtensorMap* mA = seg == 1 ? &maps.A2lo : &mapA2;
+          const CUtensorMap* mB = seg == 2 ? &maps.B2lo : &mapB2;
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          if (elect_one()) {
+            const uint32_t full = smem_u32(&bar_full[stage]);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            mbar_arrive_expect_tx(full, stage_bytes);
+            tma_load_5d(sa, mA, full, c2 * 64, ph & 1, w0, ph >> 1, h0);
+            tma_load_3d(sa + kATileBytes, mB, full, c2 * 64, n0, 0);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -469,8 +503,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
       if (p.trace && blockIdx.x == 0 && it < 16 && lane == 0) p.trace[it * 16 + 9] = clock64();
       const uint32_t d_tmem = tmem_base + as * kAccStride;
       for (int k = 0; k < kiters_all; ++k) {
-        const int c = k % p.kchunks;
-        const int kvalid = k < kiters ? min(64, p.Cin - c * 64) : min(64, p.Cin2 - (k - kiters) * 64);
+        const int kl = p.split ? static_cast<int>(fast_div(k, 0x55555556u)) : k;   // logical K chunk (k / 3 in split mode)
+        const int c = kl % p.kchunks;
+        const int kvalid = kl < kiters ? min(64, p.Cin - c * 64) : min(64, p.Cin2 - (kl - kiters) * 64);
         const int ksteps = (kvalid + 15) >> 4;
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
@@ -1272,6 +1307,14 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
       return VPB_ERR_ARG;
     }
   }
+  const bool split = a->in_lo != nullptr;
+  if (split) {
+    if (lin || !a->w_lo || (a->mode != VPB_EPI_FINAL && !a->out_lo) ||
+        ((a->mode == VPB_EPI_ADD || a->mode == VPB_EPI_MULADD) && !a->res_lo) || (a->in2 && (!a->in2_lo || !a->w2_lo))) {
+      vpb_set_error("conv: split-fp16 mode needs the TILE algorithm and the low halves of every tensor given (w_lo, out_lo, res_lo, in2_lo, w2_lo)");
+      return VPB_ERR_ARG;
+    }
+  }
   if (a->in2) {
     if (lin || a->taps != 1 || !a->w2 || a->Cin2 <= 0 || (a->Cin2 & 7) || (a->ld2 & 7) || a->ld2 < a->Cin2) {
       vpb_set_error("conv: second input needs the TILE algorithm, taps=1, w2, Cin2/ld2 multiples of 8 (Cin2=%d ld2=%d)",
@@ -1298,6 +1341,8 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.taps = a->taps; p.phases = a->phases;
   p.in_pad = a->in_pad ? 1 : 0; p.out_pad = a->out_pad ? 1 : 0; p.res_pad = a->res_pad ? 1 : 0;
   p.lin = lin ? 1 : 0;
+  p.split = split ? 1 : 0;
+  p.out_lo = a->out_lo; p.res_lo = a->res_lo;
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
@@ -1433,13 +1478,13 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     // four 128-column accumulators) whenever the N tile is at most 128 wide
     // ... and only when the fused grid still gives >= 2 waves (measured: with fewer tiles the lost
     // parallelism and the single-buffered accumulators cost more than the saved A traffic)
-    p.fuse4 = (a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1 && !a->in2 &&
+    p.fuse4 = (a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1 && !a->in2 && !split &&
                (p.tiles_h * p.tiles_w * p.tiles_n >= 2 * device_sm_count() || a->dbg_ms == 2)) ? 1 : 0;
     p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * (p.fuse4 ? 1 : p.phases);
     const size_t stage_bytes = kATileBytes + b_bytes * (p.fuse4 ? 4 : 1);
     // staged TMA-store epilogue: plain store (ConvTranspose, with or without the fused skip link) or GELU, N tile made
     // of whole 64-channel slabs; dbg_gb == 2 forces the direct-store epilogue (A/B comparison)
-    p.tma_store = (a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) && p.BN % 64 == 0 &&
+    p.tma_store = (!split && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) && p.BN % 64 == 0 &&
                    a->phases == 4 && a->dbg_gb != 2) ? 1 : 0;
     const size_t slab_bytes = p.tma_store ? static_cast<size_t>(p.BN / 64) * 128 * 128 : 0;
     int stages = static_cast<int>((kMaxDynSmem - 1024 - slab_bytes) / stage_bytes);
@@ -1472,32 +1517,40 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     // a zero-bordered input is addressed through its interior: base at pixel (1,1), padded pitch
-    const int pad = p.in_pad;
-    const size_t pitch = static_cast<size_t>(a->W + 2 * pad) * a->ldi * 2;
-    const uint8_t* base = static_cast<const uint8_t*>(a->in) + pad * pitch + static_cast<size_t>(pad) * a->ldi * 2;
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->W),
-                          static_cast<cuuint64_t>(a->H), 1};
-    cuuint64_t strides[3] = {static_cast<cuuint64_t>(a->ldi) * 2, pitch, pitch * (a->H + 2 * pad)};
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.TW), static_cast<cuuint32_t>(p.TH), 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    r = enc(&plan->mapA, dt, 4, const_cast<uint8_t*>(base), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    auto encA = [&](const void* ptr, CUtensorMap* m) {
+      const int pad = p.in_pad;
+      const size_t pitch = static_cast<size_t>(a->W + 2 * pad) * a->ldi * 2;
+      const uint8_t* base = static_cast<const uint8_t*>(ptr) + pad * pitch + static_cast<size_t>(pad) * a->ldi * 2;
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->W),
+                            static_cast<cuuint64_t>(a->H), 1};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(a->ldi) * 2, pitch, pitch * (a->H + 2 * pad)};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.TW), static_cast<cuuint32_t>(p.TH), 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      return enc(m, dt, 4, const_cast<uint8_t*>(base), dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    r = encA(a->in, &plan->mapA);
+    if (r == CUDA_SUCCESS && split) r = encA(a->in_lo, &plan->mapAlo);
   }
   if (r != CUDA_SUCCESS) {
     vpb_set_error("conv: cuTensorMapEncodeTiled(A) failed: %d", static_cast<int>(r));
     return VPB_ERR_CUDA;
   }
   {
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->Cout),
-                          static_cast<cuuint64_t>(a->taps * a->phases)};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(a->Cin) * 2,
-                             static_cast<cuuint64_t>(a->Cin) * 2 * a->Cout};
-    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(p.pair ? p.BN / 2 : p.BN), 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    r = enc(&plan->mapB, dt, 3, const_cast<void*>(a->w), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    auto encB = [&](const void* ptr, CUtensorMap* m) {
+      cuuint64_t dims[3] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->Cout),
+                            static_cast<cuuint64_t>(a->taps * a->phases)};
+      cuuint64_t strides[2] = {static_cast<cuuint64_t>(a->Cin) * 2,
+                               static_cast<cuuint64_t>(a->Cin) * 2 * a->Cout};
+      cuuint32_t box[3] = {64, static_cast<cuuint32_t>(p.pair ? p.BN / 2 : p.BN), 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      return enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    r = encB(a->w, &plan->mapB);
+    if (r == CUDA_SUCCESS && split) r = encB(a->w_lo, &plan->mapBlo);
     if (r != CUDA_SUCCESS) {
       vpb_set_error("conv: cuTensorMapEncodeTiled(B) failed: %d", static_cast<int>(r));
       return VPB_ERR_CUDA;
@@ -1506,6 +1559,9 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   plan->mapA2 = plan->mapA;
   plan->mapB2 = plan->mapB;
   plan->mapO = plan->mapA;
+  if (!split) { plan->mapAlo = plan->mapA; plan->mapBlo = plan->mapB; }
+  plan->mapA2lo = plan->mapAlo;
+  plan->mapB2lo = plan->mapBlo;
   if (p.tma_store) {
     // output viewed as [h][a][w][b][c] (ConvTranspose phase (a,b) of pixel tile (h0,w0) is one tiled box)
     const int s2 = a->phases == 4 ? 2 : 1;
@@ -1528,31 +1584,39 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   if (a->in2) {
     // second input at output resolution, viewed as [h][a][w][b][c] (s = 2 for a ConvTranspose,
     // a = b = 0 and s = 1 otherwise); box = one pixel tile of one phase
-    const int s2 = a->phases == 4 ? 2 : 1;
-    const int pad = a->in2_pad ? 1 : 0;
-    const size_t px = static_cast<size_t>(a->ld2) * 2;                       // bytes per pixel
-    const size_t pitch = static_cast<size_t>(a->W * s2 + 2 * pad) * px;      // bytes per image row
-    const uint8_t* base = static_cast<const uint8_t*>(a->in2) + pad * pitch + pad * px;
-    cuuint64_t dims[5] = {static_cast<cuuint64_t>(a->Cin2), static_cast<cuuint64_t>(s2),
-                          static_cast<cuuint64_t>(a->W), static_cast<cuuint64_t>(s2),
-                          static_cast<cuuint64_t>(a->H)};
-    cuuint64_t strides[4] = {px, px * s2, pitch, pitch * s2};
-    cuuint32_t box[5] = {64, 1, static_cast<cuuint32_t>(p.TW), 1, static_cast<cuuint32_t>(p.TH)};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    r = enc(&plan->mapA2, dt, 5, const_cast<uint8_t*>(base), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    auto encA2 = [&](const void* ptr, CUtensorMap* m) {
+      const int s2 = a->phases == 4 ? 2 : 1;
+      const int pad = a->in2_pad ? 1 : 0;
+      const size_t px = static_cast<size_t>(a->ld2) * 2;                       // bytes per pixel
+      const size_t pitch = static_cast<size_t>(a->W * s2 + 2 * pad) * px;      // bytes per image row
+      const uint8_t* base = static_cast<const uint8_t*>(ptr) + pad * pitch + pad * px;
+      cuuint64_t dims[5] = {static_cast<cuuint64_t>(a->Cin2), static_cast<cuuint64_t>(s2),
+                            static_cast<cuuint64_t>(a->W), static_cast<cuuint64_t>(s2),
+                            static_cast<cuuint64_t>(a->H)};
+      cuuint64_t strides[4] = {px, px * s2, pitch, pitch * s2};
+      cuuint32_t box[5] = {64, 1, static_cast<cuuint32_t>(p.TW), 1, static_cast<cuuint32_t>(p.TH)};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      return enc(m, dt, 5, const_cast<uint8_t*>(base), dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    r = encA2(a->in2, &plan->mapA2);
+    if (r == CUDA_SUCCESS && split) r = encA2(a->in2_lo, &plan->mapA2lo);
     if (r != CUDA_SUCCESS) {
       vpb_set_error("conv: cuTensorMapEncodeTiled(A2) failed: %d", static_cast<int>(r));
       return VPB_ERR_CUDA;
     }
-    cuuint64_t bd[3] = {static_cast<cuuint64_t>(a->Cin2), static_cast<cuuint64_t>(a->Cout), 1};
-    cuuint64_t bs[2] = {static_cast<cuuint64_t>(a->Cin2) * 2, static_cast<cuuint64_t>(a->Cin2) * 2 * a->Cout};
-    cuuint32_t bb[3] = {64, static_cast<cuuint32_t>(p.BN), 1};
-    cuuint32_t be[3] = {1, 1, 1};
-    r = enc(&plan->mapB2, dt, 3, const_cast<void*>(a->w2), bd, bs, bb, be,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    auto encB2 = [&](const void* ptr, CUtensorMap* m) {
+      cuuint64_t bd[3] = {static_cast<cuuint64_t>(a->Cin2), static_cast<cuuint64_t>(a->Cout), 1};
+      cuuint64_t bs[2] = {static_cast<cuuint64_t>(a->Cin2) * 2, static_cast<cuuint64_t>(a->Cin2) * 2 * a->Cout};
+      cuuint32_t bb[3] = {64, static_cast<cuuint32_t>(p.BN), 1};
+      cuuint32_t be[3] = {1, 1, 1};
+      return enc(m, dt, 3, const_cast<void*>(ptr), bd, bs, bb, be,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    r = encB2(a->w2, &plan->mapB2);
+    if (r == CUDA_SUCCESS && split) r = encB2(a->w2_lo, &plan->mapB2lo);
     if (r != CUDA_SUCCESS) {
       vpb_set_error("conv: cuTensorMapEncodeTiled(B2) failed: %d", static_cast<int>(r));
       return VPB_ERR_CUDA;
@@ -1589,8 +1653,11 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     if (bf) VPB_CUDA_OK(launch_k(conv3x3_lin_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
     else VPB_CUDA_OK(launch_k(conv3x3_lin_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->p));
   } else {
-    if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->mapA2, plan->mapB2, plan->mapO, plan->p));
-    else VPB_CUDA_OK(launch_k(conv_gemm_kernel<F16>, g, b, plan->smem_bytes, stream, plan->mapA, plan->mapB, plan->mapA2, plan->mapB2, plan->mapO, plan->p));
+    ConvMaps maps;
+    maps.A = plan->mapA; maps.B = plan->mapB; maps.A2 = plan->mapA2; maps.B2 = plan->mapB2; maps.O = plan->mapO;
+    maps.Alo = plan->mapAlo; maps.Blo = plan->mapBlo; maps.A2lo = plan->mapA2lo; maps.B2lo = plan->mapB2lo;
+    if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, maps, plan->p));
+    else VPB_CUDA_OK(launch_k(conv_gemm_kernel<F16>, g, b, plan->smem_bytes, stream, maps, plan->p));
   }
   return VPB_OK;
 }

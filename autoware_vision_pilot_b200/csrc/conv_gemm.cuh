@@ -21,6 +21,9 @@ struct ConvKParams {
   int lin;                       // 1 = linear-padded 3x3 kernel
   int fuse4;                     // tile kernel, ConvTranspose: all 4 phases per CTA tile
   int tma_store;                 // tile kernel: epilogue stages the tile in shared memory and writes it with TMA stores
+  int split;                     // tile kernel: split-fp16 mode, 3 K segments (A_hi W_hi, A_lo W_hi, A_hi W_lo), hi/lo outputs
+  void* out_lo;                  // split mode: low halves of out / res (same layout as the hi tensors)
+  const void* res_lo;
   int na, nb;                    // linear kernel: activation-segment / weight-slot ring depths
   int gb;                        // linear kernel: weight tiles per slot (3 = one kernel row per barrier)
   int ms;                        // linear kernel: M sub-tiles (of 128 pixels) per CTA tile, 1, 2 or 4
@@ -41,10 +44,19 @@ struct ConvKParams {
   unsigned long long* trace;     // experiment hook (tile kernel): clock64() stamps of CTA 0, [16 tiles][16]
 };
 
+// Tensor maps of the tile kernel, passed as ONE __grid_constant__ parameter (TMA reads them from param space).
+struct ConvMaps {
+  CUtensorMap A, B;              // activations / weights
+  CUtensorMap A2, B2;            // second 1x1 input and its weights (copies of A / B when unused)
+  CUtensorMap O;                 // output view [h][a][w][b][c] for the TMA-store epilogue (copy of A when unused)
+  CUtensorMap Alo, Blo, A2lo, B2lo;   // split-fp16 mode: the low halves (copies of the hi maps when unused)
+};
+
 struct ConvPlan {
   CUtensorMap mapA, mapB;
   CUtensorMap mapA2, mapB2;      // second 1x1 input and its weights (copies of mapA/mapB when unused)
   CUtensorMap mapO;              // output view [h][a][w][b][c] for the TMA-store epilogue (copy of mapA when unused)
+  CUtensorMap mapAlo, mapBlo, mapA2lo, mapB2lo;
   ConvKParams p;
   int dtype;
   int grid;

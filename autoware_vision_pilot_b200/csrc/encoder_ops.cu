@@ -16,10 +16,12 @@ namespace vpb {
 
 // ------------------------------------------------------------------ stem conv 3x3 s2, 3 -> 32
 template <class E>
-__global__ void __launch_bounds__(128) stem_conv_kernel(const uint2* __restrict__ in, int H, int W,
+__global__ void __launch_bounds__(128) stem_conv_kernel(const uint2* __restrict__ in, const uint2* __restrict__ in_lo,
+                                                         int H, int W,
                                                          const float* __restrict__ w,
                                                          const float* __restrict__ bias,
-                                                         uint4* __restrict__ out, int Ho, int Wo) {
+                                                         uint4* __restrict__ out, uint4* __restrict__ out_lo,
+                                                         int Ho, int Wo) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sw[27 * 32];
@@ -42,7 +44,11 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const uint2* __restrict_
       const int ix = 2 * ox - 1 + kx;
       if (ix < 0 || ix >= W) continue;
       const uint2 px = __ldg(in + static_cast<size_t>(iy) * W + ix);
-      const float2 a = unpack2<E>(px.x), b = unpack2<E>(px.y);
+      float2 a = unpack2<E>(px.x), b = unpack2<E>(px.y);
+      if (in_lo) {
+        const uint2 pl = __ldg(in_lo + static_cast<size_t>(iy) * W + ix);
+        a = join2<E>(px.x, pl.x); b = join2<E>(px.y, pl.y);
+      }
       const float x[3] = {a.x, a.y, b.x};
       const float* wt = sw + (ky * 3 + kx) * 3 * 32;
 #pragma unroll
@@ -54,12 +60,13 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const uint2* __restrict_
   uint4* o = out + static_cast<size_t>(idx) * 4;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    uint4 v;
-    v.x = pack2<E>(act_silu(acc[8 * j + 0]), act_silu(acc[8 * j + 1]));
-    v.y = pack2<E>(act_silu(acc[8 * j + 2]), act_silu(acc[8 * j + 3]));
-    v.z = pack2<E>(act_silu(acc[8 * j + 4]), act_silu(acc[8 * j + 5]));
-    v.w = pack2<E>(act_silu(acc[8 * j + 6]), act_silu(acc[8 * j + 7]));
+    uint4 v, l;
+    split2<E>(act_silu(acc[8 * j + 0]), act_silu(acc[8 * j + 1]), v.x, l.x);
+    split2<E>(act_silu(acc[8 * j + 2]), act_silu(acc[8 * j + 3]), v.y, l.y);
+    split2<E>(act_silu(acc[8 * j + 4]), act_silu(acc[8 * j + 5]), v.z, l.z);
+    split2<E>(act_silu(acc[8 * j + 6]), act_silu(acc[8 * j + 7]), v.w, l.w);
     o[j] = v;
+    if (out_lo) out_lo[static_cast<size_t>(idx) * 4 + j] = l;
   }
 }
 
@@ -87,11 +94,13 @@ DwGeom dw_geometry(int H, int W, int C, int k, int stride) {
   return g;
 }
 
-template <class E, int K, int S>
-__global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict__ in, int H, int W,
+template <class E, int K, int S, bool SP>
+__global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict__ in, const uint4* __restrict__ in_lo,
+                                                         int H, int W,
                                                          int C, const float* __restrict__ w,
                                                          const float* __restrict__ bias,
-                                                         uint4* __restrict__ out, int Ho, int Wo,
+                                                         uint4* __restrict__ out, uint4* __restrict__ out_lo,
+                                                         int Ho, int Wo,
                                                          long long* __restrict__ gap_acc, int G, int PPB,
                                                          int items_per_block) {
   pdl_launch_dependents();
@@ -125,10 +134,18 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict_
 #pragma unroll
       for (int cx = 0; cx < COLS; ++cx) {   // the whole row window in flight before any use
         const int ix = ox0 * S - PAD + cx;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (ix >= 0 && ix < W) v = __ldg(in + (static_cast<size_t>(iy) * W + ix) * G + cg);
-        win[cx][0] = unpack2<E>(v.x); win[cx][1] = unpack2<E>(v.y);
-        win[cx][2] = unpack2<E>(v.z); win[cx][3] = unpack2<E>(v.w);
+        uint4 v = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
+        if (ix >= 0 && ix < W) {
+          v = __ldg(in + (static_cast<size_t>(iy) * W + ix) * G + cg);
+          if (SP) vl = __ldg(in_lo + (static_cast<size_t>(iy) * W + ix) * G + cg);
+        }
+        if (SP) {
+          win[cx][0] = join2<E>(v.x, vl.x); win[cx][1] = join2<E>(v.y, vl.y);
+          win[cx][2] = join2<E>(v.z, vl.z); win[cx][3] = join2<E>(v.w, vl.w);
+        } else {
+          win[cx][0] = unpack2<E>(v.x); win[cx][1] = unpack2<E>(v.y);
+          win[cx][2] = unpack2<E>(v.z); win[cx][3] = unpack2<E>(v.w);
+        }
       }
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
@@ -155,8 +172,15 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict_
 #pragma unroll
       for (int i = 0; i < 8; ++i) sum[i] += v[i];
       uint4 o;
-      o.x = pack2<E>(v[0], v[1]); o.y = pack2<E>(v[2], v[3]);
-      o.z = pack2<E>(v[4], v[5]); o.w = pack2<E>(v[6], v[7]);
+      if (SP) {
+        uint4 l;
+        split2<E>(v[0], v[1], o.x, l.x); split2<E>(v[2], v[3], o.y, l.y);
+        split2<E>(v[4], v[5], o.z, l.z); split2<E>(v[6], v[7], o.w, l.w);
+        out_lo[(static_cast<size_t>(oy) * Wo + ox) * G + cg] = l;
+      } else {
+        o.x = pack2<E>(v[0], v[1]); o.y = pack2<E>(v[2], v[3]);
+        o.z = pack2<E>(v[4], v[5]); o.w = pack2<E>(v[6], v[7]);
+      }
       out[(static_cast<size_t>(oy) * Wo + ox) * G + cg] = o;
     }
   }
@@ -191,6 +215,7 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
                                                         const float* __restrict__ b2,
                                                         const float* __restrict__ w_proj, int Cout,
                                                         typename E::T* __restrict__ w_scaled,
+                                                        typename E::T* __restrict__ w_scaled_lo,
                                                         float* __restrict__ scale_out) {
   pdl_launch_dependents();
   pdl_wait();
@@ -261,10 +286,11 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
     const float4 a = __ldg(reinterpret_cast<const float4*>(w_proj) + 2 * i);
     const float4 b = __ldg(reinterpret_cast<const float4*>(w_proj) + 2 * i + 1);
     const float* g = gate + k8;
-    uint4 o;
-    o.x = pack2<E>(a.x * g[0], a.y * g[1]); o.y = pack2<E>(a.z * g[2], a.w * g[3]);
-    o.z = pack2<E>(b.x * g[4], b.y * g[5]); o.w = pack2<E>(b.z * g[6], b.w * g[7]);
+    uint4 o, l;
+    split2<E>(a.x * g[0], a.y * g[1], o.x, l.x); split2<E>(a.z * g[2], a.w * g[3], o.y, l.y);
+    split2<E>(b.x * g[4], b.y * g[5], o.z, l.z); split2<E>(b.z * g[6], b.w * g[7], o.w, l.w);
     reinterpret_cast<uint4*>(w_scaled)[i] = o;
+    if (w_scaled_lo) reinterpret_cast<uint4*>(w_scaled_lo)[i] = l;
   }
 }
 
@@ -274,7 +300,8 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
 // fixed order (deterministic).  The first version walked the pixels serially per channel: 16 us for the
 // 200 x 1280 context input, all of it load latency on every trunk's critical path.
 template <class E>
-__global__ void __launch_bounds__(256) gap_kernel(const typename E::T* __restrict__ in, int HW, int C, int ld,
+__global__ void __launch_bounds__(256) gap_kernel(const typename E::T* __restrict__ in,
+                                                  const typename E::T* __restrict__ in_lo, int HW, int C, int ld,
                                                   float* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
@@ -295,8 +322,18 @@ __global__ void __launch_bounds__(256) gap_kernel(const typename E::T* __restric
           const float2 f = unpack2<E>(w[i]);
           acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
         }
+        if (in_lo) {
+          const uint4 vl = __ldg(reinterpret_cast<const uint4*>(in_lo + static_cast<size_t>(p) * ld + c0));
+          const uint32_t wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack2<E>(wl[i]);
+            acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
+          }
+        }
       } else {
-        for (int i = 0; i < 8 && c0 + i < C; ++i) acc[i] += to_f32<E>(src[i]);
+        for (int i = 0; i < 8 && c0 + i < C; ++i)
+          acc[i] += to_f32<E>(src[i]) + (in_lo ? to_f32<E>(in_lo[static_cast<size_t>(p) * ld + c0 + i]) : 0.f);
       }
     }
   }
@@ -340,7 +377,7 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
 template <class E>
 __global__ void ctx_conv1_kernel(const float* __restrict__ in, int H, int W,
                                  const float* __restrict__ w, const float* __restrict__ b, int Cout,
-                                 typename E::T* __restrict__ out, int out_pad) {
+                                 typename E::T* __restrict__ out, typename E::T* __restrict__ out_lo, int out_pad) {
   pdl_launch_dependents();
   pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,7 +392,11 @@ __global__ void ctx_conv1_kernel(const float* __restrict__ in, int H, int W,
       const int iy = y - 1 + ky, ix = x - 1 + kx;
       if (iy >= 0 && iy < H && ix >= 0 && ix < W) s = fmaf(in[iy * W + ix], w[co * 9 + ky * 3 + kx], s);
     }
-  out[(static_cast<size_t>(y + out_pad) * (W + 2 * out_pad) + (x + out_pad)) * Cout + co] = from_f32<E>(act_gelu(s));
+  const size_t oi = (static_cast<size_t>(y + out_pad) * (W + 2 * out_pad) + (x + out_pad)) * Cout + co;
+  const float g = act_gelu(s);
+  const typename E::T hi = from_f32<E>(g);
+  out[oi] = hi;
+  if (out_lo) out_lo[oi] = from_f32<E>(g - to_f32<E>(hi));
 }
 
 // ------------------------------------------------------------------ max-pool feature fusion
@@ -367,7 +408,11 @@ __global__ void __launch_bounds__(256) fuse_pool_kernel(const uint4* __restrict_
                                                          const uint4* __restrict__ f2,
                                                          const uint4* __restrict__ f3,
                                                          const uint4* __restrict__ f4, int H4, int W4,
-                                                         uint4* __restrict__ out) {
+                                                         uint4* __restrict__ out,
+                                                         // split-fp16 mode: byte offsets from each hi tensor to its lo half
+                                                         // (0 = 16-bit mode), and the lo half of the output
+                                                         size_t lo0, size_t lo1, size_t lo2, size_t lo3, size_t lo4,
+                                                         uint4* __restrict__ out_lo) {
   pdl_launch_dependents();
   pdl_wait();
   // channel-group layout of the output pixel: [f0:4 | f1:3 | f2:5 | f3:10 | f4:160] = 182 groups
@@ -377,20 +422,25 @@ __global__ void __launch_bounds__(256) fuse_pool_kernel(const uint4* __restrict_
   if (gw >= H4 * W4 * kGroups) return;
   const int g = gw % kGroups, pix = gw / kGroups;
   const int y = pix / W4, x = pix - y * W4;
-  const uint4* src; int win, G, cg;
-  if (g < 4) { src = f0; win = 16; G = 4; cg = g; }
-  else if (g < 7) { src = f1; win = 8; G = 3; cg = g - 4; }
-  else if (g < 12) { src = f2; win = 4; G = 5; cg = g - 7; }
-  else if (g < 22) { src = f3; win = 2; G = 10; cg = g - 12; }
-  else { src = f4; win = 1; G = 160; cg = g - 22; }
+  const uint4* src; int win, G, cg; size_t lo_off;
+  if (g < 4) { src = f0; win = 16; G = 4; cg = g; lo_off = lo0; }
+  else if (g < 7) { src = f1; win = 8; G = 3; cg = g - 4; lo_off = lo1; }
+  else if (g < 12) { src = f2; win = 4; G = 5; cg = g - 7; lo_off = lo2; }
+  else if (g < 22) { src = f3; win = 2; G = 10; cg = g - 12; lo_off = lo3; }
+  else { src = f4; win = 1; G = 160; cg = g - 22; lo_off = lo4; }
   const int Ws = W4 * win;
   float m[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
   for (int t = lane; t < win * win; t += 32) {
     const int wy = t / win, wx = t - wy * win;
-    const uint4 v = __ldg(src + (static_cast<size_t>(y * win + wy) * Ws + (x * win + wx)) * G + cg);
-    const float2 a = unpack2<E>(v.x), b = unpack2<E>(v.y), c = unpack2<E>(v.z), d = unpack2<E>(v.w);
+    const uint4* sp = src + (static_cast<size_t>(y * win + wy) * Ws + (x * win + wx)) * G + cg;
+    const uint4 v = __ldg(sp);
+    float2 a = unpack2<E>(v.x), b = unpack2<E>(v.y), c = unpack2<E>(v.z), d = unpack2<E>(v.w);
+    if (out_lo) {     // hi + lo is exact in fp32, so the max of the sums is the max of the stored values
+      const uint4 vl = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(sp) + lo_off));
+      a = join2<E>(v.x, vl.x); b = join2<E>(v.y, vl.y); c = join2<E>(v.z, vl.z); d = join2<E>(v.w, vl.w);
+    }
     m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], b.x); m[3] = fmaxf(m[3], b.y);
     m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], d.x); m[7] = fmaxf(m[7], d.y);
   }
@@ -399,10 +449,11 @@ __global__ void __launch_bounds__(256) fuse_pool_kernel(const uint4* __restrict_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], o));
   if (lane == 0) {
-    uint4 o;
-    o.x = pack2<E>(m[0], m[1]); o.y = pack2<E>(m[2], m[3]);
-    o.z = pack2<E>(m[4], m[5]); o.w = pack2<E>(m[6], m[7]);
+    uint4 o, l;
+    split2<E>(m[0], m[1], o.x, l.x); split2<E>(m[2], m[3], o.y, l.y);
+    split2<E>(m[4], m[5], o.z, l.z); split2<E>(m[6], m[7], o.w, l.w);
     out[static_cast<size_t>(pix) * kGroups + g] = o;
+    if (out_lo) out_lo[static_cast<size_t>(pix) * kGroups + g] = l;
   }
 }
 
@@ -416,34 +467,50 @@ using namespace vpb;
     else KERNEL<F16> __VA_ARGS__;              \
   } while (0)
 
-extern "C" int vpb_stem_conv(int dtype, const void* in, int H, int W, const float* w,
-                             const float* bias, void* out, void* stream) {
+// `*_lo` arguments of the *_x launchers: the low halves of split-fp16 tensors (NULL = plain 16-bit mode).
+int vpb::stem_conv_x(int dtype, const void* in, const void* in_lo, int H, int W, const float* w, const float* bias,
+                     void* out, void* out_lo, cudaStream_t st) {
   const int Ho = H / 2, Wo = W / 2;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = Ho * Wo;
   const dim3 g((n + 127) / 128), b(128);
   if (dtype == VPB_BF16)
-    VPB_CUDA_OK(launch_k(stem_conv_kernel<BF16>, g, b, 0, st, static_cast<const uint2*>(in), H, W, w, bias, static_cast<uint4*>(out), Ho, Wo));
+    VPB_CUDA_OK(launch_k(stem_conv_kernel<BF16>, g, b, 0, st, static_cast<const uint2*>(in), static_cast<const uint2*>(in_lo), H, W, w, bias, static_cast<uint4*>(out), static_cast<uint4*>(out_lo), Ho, Wo));
   else
-    VPB_CUDA_OK(launch_k(stem_conv_kernel<F16>, g, b, 0, st, static_cast<const uint2*>(in), H, W, w, bias, static_cast<uint4*>(out), Ho, Wo));
+    VPB_CUDA_OK(launch_k(stem_conv_kernel<F16>, g, b, 0, st, static_cast<const uint2*>(in), static_cast<const uint2*>(in_lo), H, W, w, bias, static_cast<uint4*>(out), static_cast<uint4*>(out_lo), Ho, Wo));
   return VPB_OK;
+}
+extern "C" int vpb_stem_conv(int dtype, const void* in, int H, int W, const float* w,
+                             const float* bias, void* out, void* stream) {
+  return vpb::stem_conv_x(dtype, in, nullptr, H, W, w, bias, out, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vpb_depthwise(int dtype, const void* in, int H, int W, int C, int k, int stride,
                              const float* w, const float* bias, void* out, long long* gap_acc,
                              void* stream) {
+  return vpb::depthwise_x(dtype, in, nullptr, H, W, C, k, stride, w, bias, out, nullptr, gap_acc, static_cast<cudaStream_t>(stream));
+}
+int vpb::depthwise_x(int dtype, const void* in, const void* in_lo, int H, int W, int C, int k, int stride,
+                     const float* w, const float* bias, void* out, void* out_lo, long long* gap_acc,
+                     cudaStream_t st) {
   if ((C & 7) || (k != 3 && k != 5) || (stride != 1 && stride != 2) || C > 2048) {
     vpb_set_error("depthwise: unsupported C=%d k=%d stride=%d", C, k, stride);
     return VPB_ERR_ARG;
   }
   const DwGeom g = dw_geometry(H, W, C, k, stride);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = static_cast<size_t>(g.PPB) * C * sizeof(float);
   const uint4* i4 = static_cast<const uint4*>(in);
+  const uint4* i4l = static_cast<const uint4*>(in_lo);
   uint4* o4 = static_cast<uint4*>(out);
+  uint4* o4l = static_cast<uint4*>(out_lo);
+  const bool sp = in_lo != nullptr;
+  if (sp && !out_lo) { vpb_set_error("depthwise: split mode needs out_lo"); return VPB_ERR_ARG; }
 #define DW_LAUNCH(E, K, S)                                                                             \
-  VPB_CUDA_OK(launch_k(depthwise_kernel<E, K, S>, dim3(g.nblocks), dim3(g.threads), smem, st, i4, H, W, C, \
-                       w, bias, o4, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block))
+  do {                                                                                                 \
+    if (sp) VPB_CUDA_OK(launch_k(depthwise_kernel<E, K, S, true>, dim3(g.nblocks), dim3(g.threads), smem, st, i4, i4l, H, W, C, \
+                                 w, bias, o4, o4l, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block));  \
+    else VPB_CUDA_OK(launch_k(depthwise_kernel<E, K, S, false>, dim3(g.nblocks), dim3(g.threads), smem, st, i4, i4l, H, W, C, \
+                              w, bias, o4, o4l, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block));     \
+  } while (0)
 #define DW_DISPATCH(E)                                            \
   do {                                                            \
     if (k == 3 && stride == 1) DW_LAUNCH(E, 3, 1);                \
@@ -461,24 +528,31 @@ extern "C" int vpb_se_scale(int dtype, const long long* gap_acc, int HW, int C, 
                             const float* w1, const float* b1, const float* w2, const float* b2,
                             const float* w_proj, int Cout, void* w_scaled, float* scale_out,
                             void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return vpb::se_scale_x(dtype, gap_acc, HW, C, sq, w1, b1, w2, b2, w_proj, Cout, w_scaled, nullptr, scale_out,
+                         static_cast<cudaStream_t>(stream));
+}
+int vpb::se_scale_x(int dtype, const long long* gap_acc, int HW, int C, int sq, const float* w1, const float* b1,
+                    const float* w2, const float* b2, const float* w_proj, int Cout, void* w_scaled,
+                    void* w_scaled_lo, float* scale_out, cudaStream_t st) {
   const size_t smem = (2 * static_cast<size_t>(C) + sq) * sizeof(float);
   const int grid = std::max(1, std::min(48, (Cout * C / 8 + 1023) / 1024));
   if (dtype == VPB_BF16)
     VPB_CUDA_OK(launch_k(se_scale_kernel<BF16>, dim3(grid), dim3(512), smem, st, gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
-                         w_proj, Cout, static_cast<__nv_bfloat16*>(w_scaled), scale_out));
+                         w_proj, Cout, static_cast<__nv_bfloat16*>(w_scaled), static_cast<__nv_bfloat16*>(w_scaled_lo), scale_out));
   else
     VPB_CUDA_OK(launch_k(se_scale_kernel<F16>, dim3(grid), dim3(512), smem, st, gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
-                         w_proj, Cout, static_cast<__half*>(w_scaled), scale_out));
+                         w_proj, Cout, static_cast<__half*>(w_scaled), static_cast<__half*>(w_scaled_lo), scale_out));
   return VPB_OK;
 }
 
 extern "C" int vpb_gap(int dtype, const void* in, int HW, int C, int ld, float* out, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return vpb::gap_x(dtype, in, nullptr, HW, C, ld, out, static_cast<cudaStream_t>(stream));
+}
+int vpb::gap_x(int dtype, const void* in, const void* in_lo, int HW, int C, int ld, float* out, cudaStream_t st) {
   if (dtype == VPB_BF16)
-    VPB_CUDA_OK(launch_k(gap_kernel<BF16>, dim3((C + 255) / 256), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(in), HW, C, ld, out));
+    VPB_CUDA_OK(launch_k(gap_kernel<BF16>, dim3((C + 255) / 256), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(in_lo), HW, C, ld, out));
   else
-    VPB_CUDA_OK(launch_k(gap_kernel<F16>, dim3((C + 255) / 256), dim3(256), 0, st, static_cast<const __half*>(in), HW, C, ld, out));
+    VPB_CUDA_OK(launch_k(gap_kernel<F16>, dim3((C + 255) / 256), dim3(256), 0, st, static_cast<const __half*>(in), static_cast<const __half*>(in_lo), HW, C, ld, out));
   return VPB_OK;
 }
 
@@ -490,23 +564,31 @@ extern "C" int vpb_linear(const float* x, const float* w, const float* b, int in
 
 extern "C" int vpb_ctx_conv1(int dtype, const float* in, int H, int W, const float* w, const float* b,
                              int Cout, void* out, int out_pad, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return vpb::ctx_conv1_x(dtype, in, H, W, w, b, Cout, out, nullptr, out_pad, static_cast<cudaStream_t>(stream));
+}
+int vpb::ctx_conv1_x(int dtype, const float* in, int H, int W, const float* w, const float* b, int Cout, void* out,
+                     void* out_lo, int out_pad, cudaStream_t st) {
   const int n = H * W * Cout;
   if (dtype == VPB_BF16)
-    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<BF16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__nv_bfloat16*>(out), out_pad));
+    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<BF16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), out_pad));
   else
-    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<F16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__half*>(out), out_pad));
+    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<F16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__half*>(out), static_cast<__half*>(out_lo), out_pad));
   return VPB_OK;
 }
 
 extern "C" int vpb_fuse_pool_concat(int dtype, const void* f0, const void* f1, const void* f2,
                                     const void* f3, const void* f4, int H4, int W4, void* out,
                                     void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t z[5] = {0, 0, 0, 0, 0};
+  return vpb::fuse_pool_x(dtype, f0, f1, f2, f3, f4, z, H4, W4, out, nullptr, static_cast<cudaStream_t>(stream));
+}
+int vpb::fuse_pool_x(int dtype, const void* f0, const void* f1, const void* f2, const void* f3, const void* f4,
+                     const size_t lo_off[5], int H4, int W4, void* out, void* out_lo, cudaStream_t st) {
   const long warps = static_cast<long>(H4) * W4 * 182;
   const int blocks = static_cast<int>((warps * 32 + 255) / 256);
 #define FP_ARGS static_cast<const uint4*>(f0), static_cast<const uint4*>(f1), static_cast<const uint4*>(f2), \
-                static_cast<const uint4*>(f3), static_cast<const uint4*>(f4), H4, W4, static_cast<uint4*>(out)
+                static_cast<const uint4*>(f3), static_cast<const uint4*>(f4), H4, W4, static_cast<uint4*>(out), \
+                lo_off[0], lo_off[1], lo_off[2], lo_off[3], lo_off[4], static_cast<uint4*>(out_lo)
   if (dtype == VPB_BF16) VPB_CUDA_OK(launch_k(fuse_pool_kernel<BF16>, dim3(blocks), dim3(256), 0, st, FP_ARGS));
   else VPB_CUDA_OK(launch_k(fuse_pool_kernel<F16>, dim3(blocks), dim3(256), 0, st, FP_ARGS));
 #undef FP_ARGS

@@ -97,6 +97,7 @@ static uint64_t hash_prefix(const WeightMap& w, const std::string& pfx) {
 // =============================================================== engine
 struct Tens {  // NHWC 16-bit activation, channel stride == C; pad = 1: zero-bordered [(H+2)*(W+2)][C]
   void* p = nullptr; int H = 0, W = 0, C = 0, pad = 0;
+  void* lo = nullptr;   // split-fp16 mode: the low half (same layout), NULL otherwise
   size_t bytes() const { return static_cast<size_t>(H + 2 * pad) * (W + 2 * pad) * C * 2; }
 };
 
@@ -144,6 +145,10 @@ struct vp_engine {
   vp_engine_config cfg{};
   int gpu_id = 0;
   bool oom = false;                       // a device / pinned allocation failed during construction
+  bool split = false;                     // VP_PREC_SPLIT: every 16-bit tensor is a (hi, lo) pair, GEMMs run 3 K segments
+  std::unordered_map<const void*, void*> lo_of;   // 16-bit weight buffer -> its low half (split mode)
+  void* lo(const void* hi) const { auto it = lo_of.find(hi); return it == lo_of.end() ? nullptr : it->second; }
+  void* d_pre_lo = nullptr;
   int dtype = VPB_F16;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -225,7 +230,8 @@ struct vp_engine {
   }
   Tens act_alloc(int H, int W, int C, int pad = 0) {
     Tens a; a.H = H; a.W = W; a.C = C; a.pad = pad;
-    a.p = dalloc(a.bytes(), false);
+    a.p = dalloc(a.bytes() * (split ? 2 : 1), false);
+    if (split && a.p) a.lo = static_cast<uint8_t*>(a.p) + a.bytes();
     return a;
   }
   float* upload_f32(const std::vector<float>& v) {
@@ -234,13 +240,22 @@ struct vp_engine {
     return p;
   }
   void* upload_16(const std::vector<float>& v) {
-    std::vector<uint16_t> h(v.size());
-    for (size_t i = 0; i < v.size(); ++i) {
-      if (dtype == VPB_BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v[i]); memcpy(&h[i], &b, 2); }
-      else { __half b = __float2half_rn(v[i]); memcpy(&h[i], &b, 2); }
+    const size_t n = v.size();
+    std::vector<uint16_t> h(split ? 2 * n : n);     // split mode: [hi | lo], lo = round16(v - hi)
+    for (size_t i = 0; i < n; ++i) {
+      if (dtype == VPB_BF16) {
+        __nv_bfloat16 b = __float2bfloat16_rn(v[i]); memcpy(&h[i], &b, 2);
+        if (split) { __nv_bfloat16 l = __float2bfloat16_rn(v[i] - __bfloat162float(b)); memcpy(&h[n + i], &l, 2); }
+      } else {
+        __half b = __float2half_rn(v[i]); memcpy(&h[i], &b, 2);
+        if (split) { __half l = __float2half_rn(v[i] - __half2float(b)); memcpy(&h[n + i], &l, 2); }
+      }
     }
     void* p = dalloc(h.size() * 2, true);
-    if (p) cudaMemcpy(p, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
+    if (p) {
+      cudaMemcpy(p, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
+      if (split) lo_of[p] = static_cast<uint8_t*>(p) + n * 2;
+    }
     return p;
   }
 
@@ -256,8 +271,15 @@ struct vp_engine {
     a.in_pad = in.pad;
     if (out) { a.out = out->p; a.ldo = out->C; a.out_pad = out->pad; }
     if (res) { a.res = res->p; a.ldr = res->C; a.res_pad = res->pad; }
-    // 3x3 on a zero-bordered input -> linear-padded kernel (one TMA segment per kernel row)
-    a.algo = (taps == 9 && in.pad) ? VPB_ALGO_LINEAR : VPB_ALGO_TILE;
+    // 3x3 on a zero-bordered input -> linear-padded kernel (one TMA segment per kernel row); the split-fp16 mode
+    // runs everything on the tile kernel (three K segments per chunk)
+    a.algo = (taps == 9 && in.pad && !split) ? VPB_ALGO_LINEAR : VPB_ALGO_TILE;
+    if (split) {
+      a.in_lo = in.lo; a.w_lo = lo(w);
+      if (out) a.out_lo = out->lo;
+      if (res) a.res_lo = res->lo;
+      if (in2) { a.in2_lo = in2->lo; a.w2_lo = lo(w2); }
+    }
     a.out_f32 = out_f32; a.out_cls = out_cls;
     if (in2) { a.in2 = in2->p; a.w2 = w2; a.Cin2 = in2->C; a.ld2 = in2->C; a.in2_pad = in2->pad; }
     auto plan = std::make_unique<ConvPlan>();
@@ -364,7 +386,8 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
   Tens x = e.act_alloc(kNetH / 2, kNetW / 2, 32);
   {
     const void* in = e.d_pre; void* o = x.p;
-    e.add_op(tag + "stem", "stem_conv_kernel", [=](cudaStream_t st) { return vpb_stem_conv(dt, in, kNetH, kNetW, d_stem, d_stem_b, o, st); },
+    const void* in_lo = e.d_pre_lo; void* o_lo = x.lo;
+    e.add_op(tag + "stem", "stem_conv_kernel", [=](cudaStream_t st) { return stem_conv_x(dt, in, in_lo, kNetH, kNetW, d_stem, d_stem_b, o, o_lo, st); },
              2.0 * x.H * x.W * 32 * 27, 2.0 * kNetH * kNetW * 4 + 2.0 * x.H * x.W * 32);
   }
   Tens stage_out[9];
@@ -401,7 +424,8 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
       long long* d_part = e.gap_alloc(ce);
       {
         const void* in = cur.p; void* o = dwo.p; const int H = cur.H, W = cur.W;
-        e.add_op(nm + "dw", "depthwise_kernel", [=](cudaStream_t st) { return vpb_depthwise(dt, in, H, W, ce, k, s_, d_dw, d_dwb, o, d_part, st); },
+        const void* in_lo = cur.lo; void* o_lo = dwo.lo;
+        e.add_op(nm + "dw", "depthwise_kernel", [=](cudaStream_t st) { return depthwise_x(dt, in, in_lo, H, W, ce, k, s_, d_dw, d_dwb, o, o_lo, d_part, st); },
                  2.0 * g.Ho * g.Wo * ce * k * k, 2.0 * H * W * ce + 2.0 * g.Ho * g.Wo * ce);
       }
       // SE gate folded into the projection weights
@@ -420,11 +444,13 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
         for (int c = 0; c < ce; ++c) proj[static_cast<size_t>(co) * ce + c] = pw->f[static_cast<size_t>(co) * ce + c] * s[co];
       float* d_proj = e.upload_f32(proj);
       float* d_pb = e.upload_f32(t);
-      void* d_wscaled = e.dalloc(static_cast<size_t>(cout) * ce * 2, false);
+      void* d_wscaled = e.dalloc(static_cast<size_t>(cout) * ce * 2 * (e.split ? 2 : 1), false);
+      void* d_wscaled_lo = (e.split && d_wscaled) ? static_cast<uint8_t*>(d_wscaled) + static_cast<size_t>(cout) * ce * 2 : nullptr;
+      if (d_wscaled_lo) e.lo_of[d_wscaled] = d_wscaled_lo;
       {
         const int HW = g.Ho * g.Wo;
         e.add_op(nm + "se", "se_scale_kernel", [=](cudaStream_t st) {
-          return vpb_se_scale(dt, d_part, HW, ce, sq, d_f1, d_b1, d_f2, d_b2, d_proj, cout, d_wscaled, nullptr, st);
+          return se_scale_x(dt, d_part, HW, ce, sq, d_f1, d_b1, d_f2, d_b2, d_proj, cout, d_wscaled, d_wscaled_lo, nullptr, st);
         }, 2.0 * (2.0 * ce * sq), 8.0 * ce * kGapReplicas + 8.0 * ce * sq + 4.0 * cout * ce + 2.0 * cout * ce);
       }
       // 1x1 project + BN (+ residual; StochasticDepth is identity in eval)
@@ -498,8 +524,8 @@ static int build_context(vp_engine& e, const WeightMap& w, const std::string& p,
   const int dt = e.dtype, C = feat.C, HW = feat.H * feat.W;
   float* d_v = static_cast<float*>(e.dalloc(C * 4, false));
   {
-    const void* in = feat.p;
-    e.add_op(tag + "gap", "gap_kernel", [=](cudaStream_t st) { return vpb_gap(dt, in, HW, C, C, d_v, st); }, 0.0, 2.0 * HW * C);
+    const void* in = feat.p; const void* in_lo = feat.lo;
+    e.add_op(tag + "gap", "gap_kernel", [=](cudaStream_t st) { return gap_x(dt, in, in_lo, HW, C, C, d_v, st); }, 0.0, 2.0 * HW * C);
   }
   const int dims[4] = {C, 800, 800, 200};
   const int acts[3] = {ACT_GELU, ACT_GELU, ACT_SIGMOID};
@@ -521,8 +547,8 @@ static int build_context(vp_engine& e, const WeightMap& w, const std::string& p,
   float *d_w3 = e.upload_f32(w3->f), *d_b3 = e.upload_f32(b3->f);
   Tens c4 = e.act_alloc(feat.H, feat.W, 128, /*pad=*/1);
   {
-    const float* xin = cur; void* o = c4.p; const int H = feat.H, W = feat.W;
-    e.add_op(tag + "ctx3", "ctx_conv1_kernel", [=](cudaStream_t st) { return vpb_ctx_conv1(dt, xin, H, W, d_w3, d_b3, 128, o, 1, st); },
+    const float* xin = cur; void* o = c4.p; void* o_lo = c4.lo; const int H = feat.H, W = feat.W;
+    e.add_op(tag + "ctx3", "ctx_conv1_kernel", [=](cudaStream_t st) { return ctx_conv1_x(dt, xin, H, W, d_w3, d_b3, 128, o, o_lo, 1, st); },
              2.0 * HW * 128 * 9, 2.0 * (H + 2) * (W + 2) * 128);
   }
   Tens c5, c6;
@@ -624,8 +650,11 @@ static int build_model(vp_engine& e, int idx, int kind, const WeightMap& w) {
     if (kind == VP_EGO_LANES) {  // BackboneFeatureFusion (backbone_feature_fusion.py:13-38)
       feat = e.act_alloc(enc.f[4].H, enc.f[4].W, 1456);
       const int dt = e.dtype; const void *f0 = enc.f[0].p, *f1 = enc.f[1].p, *f2 = enc.f[2].p, *f3 = enc.f[3].p, *f4 = enc.f[4].p;
-      void* o = feat.p; const int H4 = feat.H, W4 = feat.W;
-      e.add_op(tag + "fuse", "fuse_pool_kernel", [=](cudaStream_t st) { return vpb_fuse_pool_concat(dt, f0, f1, f2, f3, f4, H4, W4, o, st); },
+      void* o = feat.p; void* o_lo = feat.lo; const int H4 = feat.H, W4 = feat.W;
+      struct LoOff { size_t v[5]; } lo{};
+      for (int i = 0; i < 5; ++i)
+        lo.v[i] = enc.f[i].lo ? static_cast<size_t>(static_cast<const uint8_t*>(enc.f[i].lo) - static_cast<const uint8_t*>(enc.f[i].p)) : 0;
+      e.add_op(tag + "fuse", "fuse_pool_kernel", [=](cudaStream_t st) { return fuse_pool_x(dt, f0, f1, f2, f3, f4, lo.v, H4, W4, o, o_lo, st); },
                0.0, 2.0 * (160.0 * 320 * 32 + 80.0 * 160 * 24 + 40.0 * 80 * 40 + 20.0 * 40 * 80 + 200.0 * 1280 + 200.0 * 1456));
       e.taps[tag + "fused"] = feat;
     }
@@ -790,12 +819,19 @@ extern "C" int vp_engine_create(const vp_engine_config* cfg, vp_engine** out) {
   e->cfg = *cfg;
   e->gpu_id = cfg->gpu_id;
   e->dtype = cfg->dtype == VPB_BF16 ? VPB_BF16 : VPB_F16;
+  if (cfg->precision != VP_PREC_16 && cfg->precision != VP_PREC_SPLIT) {
+    vpb_set_error("vp_engine_create: unknown precision %d", cfg->precision);
+    return VPB_ERR_ARG;
+  }
+  e->split = cfg->precision == VP_PREC_SPLIT;
   if (cfg->stream) e->stream = static_cast<cudaStream_t>(cfg->stream);
   else { VPB_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
-  e->d_pre = e->dalloc(static_cast<size_t>(kNetH) * kNetW * 4 * 2, false);
+  e->d_pre = e->dalloc(static_cast<size_t>(kNetH) * kNetW * 4 * 2 * (e->split ? 2 : 1), false);
+  if (e->split && e->d_pre) e->d_pre_lo = static_cast<uint8_t*>(e->d_pre) + static_cast<size_t>(kNetH) * kNetW * 4 * 2;
+  e->pre.out_lo = e->d_pre_lo;
   e->d_resized = static_cast<uint8_t*>(e->dalloc(static_cast<size_t>(kNetH) * kNetW * 3, false));
   {
-    Tens pre; pre.p = e->d_pre; pre.H = kNetH; pre.W = kNetW; pre.C = 4;
+    Tens pre; pre.p = e->d_pre; pre.lo = e->d_pre_lo; pre.H = kNetH; pre.W = kNetW; pre.C = 4;
     e->taps["pre"] = pre;
   }
   for (int i = 0; i < cfg->n_models; ++i) {
@@ -979,13 +1015,14 @@ extern "C" int vp_engine_read_resized(vp_engine* e, uint8_t* dst) {
 }
 
 namespace vpb {
-template <class T> __global__ void tap_to_f32_nchw(const T* in, int H, int W, int C, int Cvalid, int pad, float* out) {
+template <class T> __global__ void tap_to_f32_nchw(const T* in, const T* in_lo, int H, int W, int C, int Cvalid, int pad, float* out) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long>(H) * W * Cvalid) return;
   const int c = static_cast<int>(i / (static_cast<long>(H) * W));
   const long pix = i - static_cast<long>(c) * H * W;
   const long y = pix / W, x = pix - y * W;
-  out[i] = static_cast<float>(in[((y + pad) * (W + 2 * pad) + (x + pad)) * C + c]);
+  const long si = ((y + pad) * (W + 2 * pad) + (x + pad)) * C + c;
+  out[i] = static_cast<float>(in[si]) + (in_lo ? static_cast<float>(in_lo[si]) : 0.f);
 }
 }  // namespace vpb
 
@@ -1007,8 +1044,8 @@ extern "C" long vp_engine_read_tap(vp_engine* e, const char* name, float* dst, l
   }
   float* d = e->d_tap_scratch;
   const int blocks = static_cast<int>((n + 255) / 256);
-  if (e->dtype == VPB_BF16) tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __nv_bfloat16*>(a.p), a.H, a.W, a.C, Cv, a.pad, d);
-  else tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __half*>(a.p), a.H, a.W, a.C, Cv, a.pad, d);
+  if (e->dtype == VPB_BF16) tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __nv_bfloat16*>(a.p), static_cast<const __nv_bfloat16*>(a.lo), a.H, a.W, a.C, Cv, a.pad, d);
+  else tap_to_f32_nchw<<<blocks, 256, 0, e->stream>>>(static_cast<const __half*>(a.p), static_cast<const __half*>(a.lo), a.H, a.W, a.C, Cv, a.pad, d);
   cudaError_t ce = cudaMemcpyAsync(dst, d, n * 4, cudaMemcpyDeviceToHost, e->stream);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
   if (ce != cudaSuccess) { vpb_set_error("read_tap: %s", cudaGetErrorString(ce)); return VPB_ERR_CUDA; }

@@ -22,6 +22,7 @@ struct PreprocessPlan {
   int rows_cap = 0, patch_w_cap = 0;
   int TY = 20, pitch = 0, xt = 16;   // Pillow kernel: output rows per block, smem row pitch (bytes), tap capacity (16 | 32)
   int device = -1;                   // device that owns d_tables
+  void* out_lo = nullptr;            // split-fp16 mode: low half of the output tensor (set once by the engine)
   size_t smem_bytes = 0;
   int* d_tables = nullptr;
   size_t off_xb = 0, off_xk = 0, off_yb = 0, off_yk = 0;
@@ -39,6 +40,21 @@ struct DwGeom {
   int Ho, Wo, G, PPB, threads, pix_per_block, nblocks;
 };
 DwGeom dw_geometry(int H, int W, int C, int k, int stride);
+
+// Launchers with the optional low halves of split-fp16 tensors (NULL / 0 = plain 16-bit mode); the extern "C"
+// entry points of vp_b200_ops.h forward to these.
+int stem_conv_x(int dtype, const void* in, const void* in_lo, int H, int W, const float* w, const float* bias,
+                void* out, void* out_lo, cudaStream_t st);
+int depthwise_x(int dtype, const void* in, const void* in_lo, int H, int W, int C, int k, int stride, const float* w,
+                const float* bias, void* out, void* out_lo, long long* gap_acc, cudaStream_t st);
+int se_scale_x(int dtype, const long long* gap_acc, int HW, int C, int sq, const float* w1, const float* b1,
+               const float* w2, const float* b2, const float* w_proj, int Cout, void* w_scaled, void* w_scaled_lo,
+               float* scale_out, cudaStream_t st);
+int gap_x(int dtype, const void* in, const void* in_lo, int HW, int C, int ld, float* out, cudaStream_t st);
+int ctx_conv1_x(int dtype, const float* in, int H, int W, const float* w, const float* b, int Cout, void* out,
+                void* out_lo, int out_pad, cudaStream_t st);
+int fuse_pool_x(int dtype, const void* f0, const void* f1, const void* f2, const void* f3, const void* f4,
+                const size_t lo_off[5], int H4, int W4, void* out, void* out_lo, cudaStream_t st);
 
 // One-time per-DEVICE initialisation (function attributes, constant tables): engines for several GPUs may
 // live in one process, and entry points may be called from several threads.

@@ -104,6 +104,7 @@ struct PreParams {
   const int* xb; const int* xk; int xks;   // horizontal bounds / coeffs / ksize
   const int* yb; const int* yk; int yks;   // vertical
   void* out;            // [OH][OW][4] 16-bit
+  void* out_lo;         // split-fp16 mode: low half of the normalised tensor (NULL otherwise)
   uint8_t* out_u8;      // optional [OH][OW][3] resized image in tensor channel order
   int OH, OW;
 };
@@ -119,15 +120,16 @@ __device__ __forceinline__ void emit_pixel(const PreParams& p, int oy, int ox, c
     v[c] = __fdiv_rn(x - p.mean[c], p.stdv[c]);
     if (p.out_u8) p.out_u8[(static_cast<size_t>(oy) * p.OW + ox) * 3 + c] = static_cast<uint8_t>(s);
   }
-  uint2 o;
-  o.x = pack2<E>(v[0], v[1]);
-  o.y = pack2<E>(v[2], 0.f);
+  uint2 o, l;
+  split2<E>(v[0], v[1], o.x, l.x);
+  split2<E>(v[2], 0.f, o.y, l.y);
   reinterpret_cast<uint2*>(p.out)[static_cast<size_t>(oy) * p.OW + ox] = o;
+  if (p.out_lo) reinterpret_cast<uint2*>(p.out_lo)[static_cast<size_t>(oy) * p.OW + ox] = l;
 }
 
 static constexpr int kTX = 32;                // output columns per block (96 output bytes per row)
 static constexpr int kTYMax = 20;             // output rows per block (runtime TY <= kTYMax, chosen by the plan)
-static constexpr int kPreThreads = 192;       // 2 x 96: one thread per output byte of a row pair in the horizontal pass
+static constexpr int kPreThreads = 384;       // 4 x 96: one thread per output byte of four rows in the horizontal pass
 static constexpr int kRowBytes = kTX * 3;     // 96
 
 // Pillow path, three phases per block (32 x TY output pixels), everything between them in shared memory:
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_pil_kernel(const PrePa
     for (int wi = lane; wi < words; wi += 32) dst[wi] = __ldg(w0 + wi);
   }
   // horizontal coefficients of this thread's output byte column -> registers
-  const int ob = tid % kRowBytes, par = tid / kRowBytes;          // par: which row of a pair
+  const int ob = tid % kRowBytes, par = tid / kRowBytes;          // par: which row of a group of kPreThreads / 96
   const int xo = ob / 3, c = ob - 3 * xo;
   const bool col_ok = ox0 + xo <= ox1;
   int K[XT];
@@ -185,13 +187,18 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_pil_kernel(const PrePa
   __syncthreads();
 
   // ---- phase 2: horizontal pass (taps beyond the filter multiply staged bytes by 0: the row pitch covers XT taps)
-  for (int r = par; r < rows; r += 2) {
+  for (int r = par; r < rows; r += kPreThreads / kRowBytes) {
     const int mis = (mis0 + (y_lo + r) * smis) & 3;
     const uint8_t* row = patch + r * pitch + mis + boff;
-    int acc = 1 << 21;
+    int acc = 1 << 21, acc1 = 0, acc2 = 0, acc3 = 0;            // four independent IMAD chains (integer: exact)
 #pragma unroll
-    for (int t = 0; t < XT; ++t) acc += K[t] * static_cast<int>(row[3 * t]);
-    acc >>= 22;
+    for (int t = 0; t < XT; t += 4) {
+      acc += K[t] * static_cast<int>(row[3 * t]);
+      acc1 += K[t + 1] * static_cast<int>(row[3 * t + 3]);
+      acc2 += K[t + 2] * static_cast<int>(row[3 * t + 6]);
+      acc3 += K[t + 3] * static_cast<int>(row[3 * t + 9]);
+    }
+    acc = (acc + acc1 + acc2 + acc3) >> 22;
     inter[r * kRowBytes + ob] = static_cast<uint8_t>(min(max(acc, 0), 255));
   }
   __syncthreads();
@@ -230,8 +237,15 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_pil_kernel(const PrePa
       const float stdv = tc == 0 ? p.stdv[0] : tc == 1 ? p.stdv[1] : p.stdv[2];     // index into the params
       const float v = __fdiv_rn(x - mean, stdv);
       const size_t pix = static_cast<size_t>(oy) * p.OW + ox;
+      const typename E::T hi = from_f32<E>(v);
       if (tc == 2) reinterpret_cast<uint32_t*>(outp)[pix * 2 + 1] = pack2<E>(v, 0.f);   // (channel 2, zero pad)
-      else outp[pix * 4 + tc] = from_f32<E>(v);
+      else outp[pix * 4 + tc] = hi;
+      if (p.out_lo) {
+        typename E::T* lop = reinterpret_cast<typename E::T*>(p.out_lo);
+        const float lo = v - to_f32<E>(hi);
+        if (tc == 2) reinterpret_cast<uint32_t*>(lop)[pix * 2 + 1] = pack2<E>(lo, 0.f);
+        else lop[pix * 4 + tc] = from_f32<E>(lo);
+      }
       if (p.out_u8) p.out_u8[pix * 3 + tc] = static_cast<uint8_t>(u[b]);
     }
   }
@@ -345,6 +359,7 @@ PreprocessPlan::~PreprocessPlan() {
 
 static void fill_params(const PreprocessPlan& pl, const uint8_t* src, int stride, int convention,
                         void* out, uint8_t* out_u8, PreParams& p) {
+  p.out_lo = pl.out_lo;
   p.src = src; p.h = pl.h; p.w = pl.w; p.stride = stride; p.mode = pl.mode;
   // conventions: see include/vp_b200_ops.h
   static const float kMeanRGB[3] = {0.485f, 0.456f, 0.406f}, kStdRGB[3] = {0.229f, 0.224f, 0.225f};

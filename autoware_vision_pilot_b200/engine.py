@@ -13,14 +13,15 @@ KIND_BY_NAME = {"scene_seg": SCENE_SEG, "scene_3d": SCENE_3D, "domain_seg": DOMA
 RESIZE_NONE, RESIZE_PIL_BICUBIC, RESIZE_CV_LINEAR = 0, 1, 2
 CONV_RGB, CONV_BGR_NOSWAP, CONV_BGR_SWAP = 0, 1, 2
 RESIZE_BY_NAME = {"none": RESIZE_NONE, "pil_bicubic": RESIZE_PIL_BICUBIC, "cv_linear": RESIZE_CV_LINEAR}
-DTYPE_BY_NAME = {"fp16": L.VPB_F16, "bf16": L.VPB_BF16}
+DTYPE_BY_NAME = {"fp16": L.VPB_F16, "bf16": L.VPB_BF16, "fp32": L.VPB_F16}
+PREC_16, PREC_SPLIT = 0, 1
 
 
 class _Config(C.Structure):
     _fields_ = [("gpu_id", C.c_int), ("dtype", C.c_int), ("resize_mode", C.c_int), ("convention", C.c_int),
                 ("n_models", C.c_int), ("kinds", C.c_int * 4), ("weights", C.c_char_p * 4),
                 ("fetch_raw", C.c_int), ("use_graph", C.c_int), ("stream", C.c_void_p),
-                ("single_stream", C.c_int)]
+                ("single_stream", C.c_int), ("precision", C.c_int)]
 
 
 class _Output(C.Structure):
@@ -80,7 +81,10 @@ class Engine:
 
     def __init__(self, kinds: Sequence[int], weights: Sequence[str], *, gpu_id: int = 0, dtype: str = "fp16",
                  resize_mode: int = RESIZE_NONE, convention: int = CONV_RGB, fetch_raw: bool = True,
-                 use_graph: bool = True, stream: Optional[int] = None, single_stream: bool = False):
+                 use_graph: bool = True, stream: Optional[int] = None, single_stream: bool = False,
+                 precision: Optional[int] = None):
+        """dtype "fp16" | "bf16": 16-bit operands; dtype "fp32" (the reference's precision="fp32") selects the
+        split-fp16 fp32-grade mode (precision=PREC_SPLIT on fp16 pairs)."""
         self._lib = _bind()
         cfg = _Config()
         cfg.gpu_id, cfg.dtype = gpu_id, DTYPE_BY_NAME[dtype]
@@ -92,6 +96,7 @@ class Engine:
         cfg.fetch_raw, cfg.use_graph = int(fetch_raw), int(use_graph)
         cfg.stream = stream
         cfg.single_stream = int(single_stream)
+        cfg.precision = (PREC_SPLIT if dtype == "fp32" else PREC_16) if precision is None else precision
         self._h = C.c_void_p()
         L.check(self._lib.vp_engine_create(C.byref(cfg), C.byref(self._h)), "vp_engine_create")
         self.kinds = list(kinds)

@@ -42,6 +42,7 @@ extern "C" {
 
 /* network kinds (the four Models/model_components network modules, e.g. scene_seg_network.py) */
 enum { VP_SCENE_SEG = 0, VP_SCENE_3D = 1, VP_DOMAIN_SEG = 2, VP_EGO_LANES = 3 };
+enum { VP_PREC_16 = 0, VP_PREC_SPLIT = 1 };
 
 typedef struct vp_engine vp_engine;
 
@@ -57,6 +58,12 @@ typedef struct {
   int use_graph;                    /* 1: replay the frame as one CUDA graph (default), 0: eager */
   void* stream;                     /* optional caller-owned cudaStream_t; NULL = engine creates one */
   int single_stream;                /* 1: no concurrent per-model lanes inside the frame graph (debug) */
+  int precision;                    /* VP_PREC_16 (default): 16-bit operands, the reference's precision="fp16"
+                                       (tensorrt_engine.hpp:53); VP_PREC_SPLIT: split-fp16 "fp32-grade" mode for the
+                                       reference's precision="fp32" engines (tensorrt_backend.cpp:129-131,
+                                       run_model_node.cpp:29-36): every tensor is a (hi, lo) fp16 pair (~22 bits), the
+                                       tcgen05 GEMMs accumulate A_hi W_hi + A_lo W_hi + A_hi W_lo in fp32 — about
+                                       3x the tensor work, results within ~1e-5 sigma of the fp32 CPU path */
 } vp_engine_config;
 
 typedef struct {

@@ -93,6 +93,18 @@ typedef struct {
                              tile, -1 = never use it, 0 = auto (small-M layers) */
   unsigned long long* dbg_trace; /* experiment hook, TILE kernel: device buffer [16 tiles][16] of clock64() stamps
                              written by CTA 0 (scripts/trace_tile.py decodes it); NULL = off */
+  /* Split-fp16 ("fp32-grade") mode, selected by in_lo != NULL (TILE algorithm; the reference's precision="fp32",
+   * tensorrt_backend.cpp:129-131): every 16-bit tensor x is the pair (x_hi = fp16(x), x_lo = fp16(x - x_hi)), ~22
+   * significant bits.  The GEMM accumulates  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  as three K segments into the same
+   * fp32 TMEM accumulator (the dropped A_lo*W_lo term is 2^-22 relative) and the epilogue writes (out, out_lo).
+   * All *_lo tensors have exactly the layout of their hi partner; res_lo / in2_lo / w2_lo are required iff the hi
+   * partner is given. */
+  const void* in_lo;
+  const void* w_lo;
+  void* out_lo;
+  const void* res_lo;
+  const void* in2_lo;
+  const void* w2_lo;
 } vpb_conv_args;
 int vpb_conv_gemm(const vpb_conv_args* a, void* stream);
 

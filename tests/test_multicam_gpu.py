@@ -44,7 +44,7 @@ def _worker(rank, world, vpw, out_dir):
     local_feat = eng.read_tap("0/fused")                               # fp32 [1456,10,20], exact 16-bit values
     # lane masks of THIS camera: synthetic lanes (the synthetic checkpoint's masks are noise); rank 1 sees no
     # right lane -> its measurement has NaN slots, the "no measurement" branch of Estimator::update
-    masks = torch.from_numpy(olat.synth_lane_masks(10 + rank, drop_right=(rank == 1))).float().cuda()
+    masks = torch.from_numpy(olat.synth_lane_masks(15 + rank, drop_right=(rank == 1))).float().cuda()
     results = []
     with torch.cuda.stream(stream):
         for it in range(2):
@@ -73,6 +73,17 @@ def test_multicamera_allgather_and_fusion(tmp_path):
     def nan_eq(a, b):
         return np.array_equal(np.nan_to_num(a, nan=-7.0), np.nan_to_num(b, nan=-7.0))
 
+    # which cameras see a valid lane pair (PathFinder runs, main.cpp:565): the CPU restatement of the lateral chain
+    from oracle import lateral as olat
+    exp_ran = []
+    for r in range(world):
+        f, t = olat.LaneFilter(), olat.LaneTracker()
+        row = []
+        for it in range(2):
+            o = f.update(olat.synth_lane_masks(15 + r, drop_right=(r == 1)))
+            row.append(bool(t.update(o.left, o.right).bev_valid))
+        exp_ran.append(row)
+    assert sum(row[0] for row in exp_ran) >= 2                        # the fusion really fuses several cameras
     exp_state = post.initial_state()
     for it in range(2):
         # what every camera contributed: its device PathFinder measurement, checked against the restatement of
@@ -83,8 +94,7 @@ def test_multicamera_allgather_and_fusion(tmp_path):
             m = lr["pf_meas"]
             assert np.isnan(m[0, 0]) and np.isnan(m[3, 0]) and np.isnan(m[13, 0])
             assert np.allclose(m[:, 1], post.pathfinder_measurement([0, 0, 0], [0, 0, 0], 0.0, 4.0)[:, 1], rtol=1e-15)
-            if r != 1:
-                assert lr["pf_ran"] == 1, f"rank {r}: PathFinder did not run on the synthetic lanes"
+            assert bool(lr["pf_ran"]) == exp_ran[r][it], f"rank {r} frame {it}: PathFinder ran {lr['pf_ran']}"
             if lr["pf_ran"]:
                 # the device measurement == path_finder.cpp:97-157 restated on this camera's own fitted curves
                 # (lane-width slot: the camera's Estimator mean before the update = 4.0 on the first frame)
