@@ -166,7 +166,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
           const typename E::T* rp = res + (px.roff + n);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            rok[c][j] = (n + 8 * j < p.ldr) && (n + 8 * j < p.ldo);
+            rok[c][j] = (n + 8 * j < p.ldr) && (n + 8 * j < p.nlim);
             rv[c][j] = rok[c][j] ? *reinterpret_cast<const uint4*>(rp + 8 * j) : make_uint4(0, 0, 0, 0);
           }
         }
@@ -193,6 +193,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
               float& b = v[c][8 * j + 2 * i + 1];
               if (p.mode == VPB_EPI_ADD) { a += f.x; b += f.y; }
               else { a = fmaf(a, f.x, f.x); b = fmaf(b, f.y, f.y); }
+              if (p.act2 == ACT_SILU) { a = act_silu(a); b = act_silu(b); }
             }
           }
       }
@@ -202,7 +203,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
         typename E::T* op = out + (px.ooff + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          if (n + 8 * j < p.ldo) {
+          if (n + 8 * j < p.nlim) {
             uint4 o;
             o.x = pack2<E>(v[c][8 * j + 0], v[c][8 * j + 1]);
             o.y = pack2<E>(v[c][8 * j + 2], v[c][8 * j + 3]);
@@ -229,7 +230,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
         typename E::T* op = out + (px.ooff + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          if (n + 8 * j < p.ldo) *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(0, 0, 0, 0);
+          if (n + 8 * j < p.nlim) *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(0, 0, 0, 0);
       }
     }
   }
@@ -344,8 +345,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_r
                                               const float* sbias, int part, const EpiPix& px) {
   // NC = 2 (two chunks per iteration) measured 2-3 % slower and makes ptxas spill in every kernel that
   // contains it (96-register cap), so only the one-chunk form is instantiated.
-  if (!p.split && p.mode == VPB_EPI_STORE && n0 + p.BN <= p.ldo && p.act == ACT_GELU) epilogue_store_fast<E, true>(p, t_row, n0, sbias, part, px);
-  else if (!p.split && p.mode == VPB_EPI_STORE && n0 + p.BN <= p.ldo && p.act == ACT_NONE) epilogue_store_fast<E, false>(p, t_row, n0, sbias, part, px);
+  if (!p.split && p.mode == VPB_EPI_STORE && n0 + p.BN <= p.nlim && p.act == ACT_GELU) epilogue_store_fast<E, true>(p, t_row, n0, sbias, part, px);
+  else if (!p.split && p.mode == VPB_EPI_STORE && n0 + p.BN <= p.nlim && p.act == ACT_NONE) epilogue_store_fast<E, false>(p, t_row, n0, sbias, part, px);
   else epilogue_chunks<E, 1>(p, t_row, n0, sbias, part, px);
 }
 
@@ -454,7 +455,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
                 if (ti < 16 && k < 4) p.trace[ti * 16 + k] = clock64();
               }
               mbar_arrive_expect_tx(full, stage_bytes);
-              tma_load_4d(sa, mA, full, c * 64, w0 + dx, h0 + dy, 0);
+              tma_load_4d(sa, mA, full, c * 64, w0 * p.stride + dx, h0 * p.stride + dy, 0);
               if (p.fuse4) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
@@ -1204,7 +1205,7 @@ conv3x3_splitk_kernel(const __grid_constant__ CUtensorMap mapA,
       const int y = static_cast<int>(fast_div(pp, p.mg_wp)), x = pp - y * p.WP;
       const bool inside = y >= 1 && y <= p.H && x >= 1 && x <= p.W;
       const int n = n0 + c4 * 4;
-      if (n >= p.ldo) continue;
+      if (n >= p.nlim) continue;
       const uint32_t upix = static_cast<uint32_t>((y - 1) * p.W + (x - 1));
       typename E::T* op = out + ((p.out_pad ? static_cast<uint32_t>(pp) : upix) * p.ldo + n);
       if (!inside) {
@@ -1283,6 +1284,17 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     vpb_set_error("conv: Cin=%d ldi=%d must be multiples of 8 (ldi >= Cin)", a->Cin, a->ldi);
     return VPB_ERR_ARG;
   }
+  const int cstride = a->stride == 2 ? 2 : 1;
+  if (a->stride != 0 && a->stride != 1 && a->stride != 2) { vpb_set_error("conv: stride %d unsupported", a->stride); return VPB_ERR_ARG; }
+  if (cstride == 2 && (a->algo == VPB_ALGO_LINEAR || a->phases != 1 || a->in_pad || a->in2 || a->in_lo)) {
+    vpb_set_error("conv: stride 2 needs the TILE algorithm on an unpadded input, phases = 1, no second input");
+    return VPB_ERR_ARG;
+  }
+  if (a->ldw != 0 && (a->ldw < a->Cin || (a->ldw & 7) || a->algo == VPB_ALGO_LINEAR)) {
+    vpb_set_error("conv: ldw=%d must be a multiple of 8 >= Cin (TILE algorithm)", a->ldw);
+    return VPB_ERR_ARG;
+  }
+  if (a->act2 != ACT_NONE && a->act2 != ACT_SILU) { vpb_set_error("conv: act2 supports SiLU only"); return VPB_ERR_ARG; }
   if (!((a->taps == 9 && a->phases == 1) || (a->taps == 1 && (a->phases == 1 || a->phases == 4)))) {
     vpb_set_error("conv: unsupported taps=%d phases=%d", a->taps, a->phases);
     return VPB_ERR_ARG;
@@ -1342,6 +1354,8 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.in_pad = a->in_pad ? 1 : 0; p.out_pad = a->out_pad ? 1 : 0; p.res_pad = a->res_pad ? 1 : 0;
   p.lin = lin ? 1 : 0;
   p.split = split ? 1 : 0;
+  p.stride = cstride; p.act2 = a->act2;
+  p.nlim = a->out_slice ? std::min(a->ldo, (a->Cout + 7) / 8 * 8) : a->ldo;
   p.out_lo = a->out_lo; p.res_lo = a->res_lo;
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
@@ -1519,13 +1533,15 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     // a zero-bordered input is addressed through its interior: base at pixel (1,1), padded pitch
     auto encA = [&](const void* ptr, CUtensorMap* m) {
       const int pad = p.in_pad;
-      const size_t pitch = static_cast<size_t>(a->W + 2 * pad) * a->ldi * 2;
+      const int Hin = (cstride == 2 && a->in_h > 0) ? a->in_h : a->H, Win = (cstride == 2 && a->in_w > 0) ? a->in_w : a->W;
+      const size_t pitch = static_cast<size_t>(Win + 2 * pad) * a->ldi * 2;
       const uint8_t* base = static_cast<const uint8_t*>(ptr) + pad * pitch + static_cast<size_t>(pad) * a->ldi * 2;
-      cuuint64_t dims[4] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->W),
-                            static_cast<cuuint64_t>(a->H), 1};
-      cuuint64_t strides[3] = {static_cast<cuuint64_t>(a->ldi) * 2, pitch, pitch * (a->H + 2 * pad)};
-      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.TW), static_cast<cuuint32_t>(p.TH), 1};
-      cuuint32_t es[4] = {1, 1, 1, 1};
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(Win),
+                            static_cast<cuuint64_t>(Hin), 1};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(a->ldi) * 2, pitch, pitch * (Hin + 2 * pad)};
+      // stride 2: the box spans 2*TW x 2*TH input pixels and is traversed with element stride 2 (TW x TH loaded)
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.TW * cstride), static_cast<cuuint32_t>(p.TH * cstride), 1};
+      cuuint32_t es[4] = {1, static_cast<cuuint32_t>(cstride), static_cast<cuuint32_t>(cstride), 1};
       return enc(m, dt, 4, const_cast<uint8_t*>(base), dims, strides, box, es,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1539,10 +1555,10 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   }
   {
     auto encB = [&](const void* ptr, CUtensorMap* m) {
+      const size_t ldw = a->ldw > 0 ? a->ldw : a->Cin;
       cuuint64_t dims[3] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->Cout),
                             static_cast<cuuint64_t>(a->taps * a->phases)};
-      cuuint64_t strides[2] = {static_cast<cuuint64_t>(a->Cin) * 2,
-                               static_cast<cuuint64_t>(a->Cin) * 2 * a->Cout};
+      cuuint64_t strides[2] = {static_cast<cuuint64_t>(ldw) * 2, static_cast<cuuint64_t>(ldw) * 2 * a->Cout};
       cuuint32_t box[3] = {64, static_cast<cuuint32_t>(p.pair ? p.BN / 2 : p.BN), 1};
       cuuint32_t es[3] = {1, 1, 1};
       return enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, es,
@@ -1569,7 +1585,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     const size_t px = static_cast<size_t>(a->ldo) * 2;
     const size_t pitch = static_cast<size_t>(a->W * s2 + 2 * pad) * px;
     uint8_t* base = static_cast<uint8_t*>(a->out) + pad * pitch + pad * px;
-    cuuint64_t dims[5] = {static_cast<cuuint64_t>(a->ldo), static_cast<cuuint64_t>(s2), static_cast<cuuint64_t>(a->W),
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(p.nlim), static_cast<cuuint64_t>(s2), static_cast<cuuint64_t>(a->W),
                           static_cast<cuuint64_t>(s2), static_cast<cuuint64_t>(a->H)};
     cuuint64_t strides[4] = {px, px * s2, pitch, pitch * s2};
     cuuint32_t box[5] = {64, 1, static_cast<cuuint32_t>(p.TW), 1, static_cast<cuuint32_t>(p.TH)};

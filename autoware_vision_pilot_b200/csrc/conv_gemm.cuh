@@ -21,6 +21,9 @@ struct ConvKParams {
   int lin;                       // 1 = linear-padded 3x3 kernel
   int fuse4;                     // tile kernel, ConvTranspose: all 4 phases per CTA tile
   int tma_store;                 // tile kernel: epilogue stages the tile in shared memory and writes it with TMA stores
+  int nlim;                      // channels of an output row that may be written: ldo, or round8(Cout) for a channel SLICE
+  int stride;                    // tile kernel: 1 | 2 (input sampled through the tensor map's traversal stride)
+  int act2;                      // activation after the residual step (ADD / MULADD), ACT_NONE = off
   int split;                     // tile kernel: split-fp16 mode, 3 K segments (A_hi W_hi, A_lo W_hi, A_hi W_lo), hi/lo outputs
   void* out_lo;                  // split mode: low halves of out / res (same layout as the hi tensors)
   const void* res_lo;

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict_
                                                          uint4* __restrict__ out, uint4* __restrict__ out_lo,
                                                          int Ho, int Wo,
                                                          long long* __restrict__ gap_acc, int G, int PPB,
-                                                         int items_per_block) {
+                                                         int items_per_block, int act) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float red[];  // [PPB][C]
@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict_
       float v[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        v[2 * i] = act_silu(acc[xo][i].x);
-        v[2 * i + 1] = act_silu(acc[xo][i].y);
+        v[2 * i] = act ? act_silu(acc[xo][i].x) : acc[xo][i].x;
+        v[2 * i + 1] = act ? act_silu(acc[xo][i].y) : acc[xo][i].y;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) sum[i] += v[i];
@@ -369,6 +369,10 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
     if (act == ACT_GELU) s = act_gelu(s);
     else if (act == ACT_SIGMOID) s = 1.0f / (1.0f + expf(-s));
     else if (act == ACT_SILU) s = s / (1.0f + expf(-s));
+    else if (act == 4 /* VPB_ACT_SILU2: SiLU(SiLU(x)), CTX block common_layers.py:218-221 */) {
+      s = s / (1.0f + expf(-s));
+      s = s / (1.0f + expf(-s));
+    }
     y[o] = s;
   }
 }
@@ -377,7 +381,8 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
 template <class E>
 __global__ void ctx_conv1_kernel(const float* __restrict__ in, int H, int W,
                                  const float* __restrict__ w, const float* __restrict__ b, int Cout,
-                                 typename E::T* __restrict__ out, typename E::T* __restrict__ out_lo, int out_pad) {
+                                 typename E::T* __restrict__ out, typename E::T* __restrict__ out_lo, int out_pad,
+                                 int act) {
   pdl_launch_dependents();
   pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,7 +398,7 @@ __global__ void ctx_conv1_kernel(const float* __restrict__ in, int H, int W,
       if (iy >= 0 && iy < H && ix >= 0 && ix < W) s = fmaf(in[iy * W + ix], w[co * 9 + ky * 3 + kx], s);
     }
   const size_t oi = (static_cast<size_t>(y + out_pad) * (W + 2 * out_pad) + (x + out_pad)) * Cout + co;
-  const float g = act_gelu(s);
+  const float g = act == ACT_SILU ? s / (1.0f + expf(-s)) : act_gelu(s);
   const typename E::T hi = from_f32<E>(g);
   out[oi] = hi;
   if (out_lo) out_lo[oi] = from_f32<E>(g - to_f32<E>(hi));
@@ -491,7 +496,7 @@ extern "C" int vpb_depthwise(int dtype, const void* in, int H, int W, int C, int
 }
 int vpb::depthwise_x(int dtype, const void* in, const void* in_lo, int H, int W, int C, int k, int stride,
                      const float* w, const float* bias, void* out, void* out_lo, long long* gap_acc,
-                     cudaStream_t st) {
+                     cudaStream_t st, int act) {
   if ((C & 7) || (k != 3 && k != 5) || (stride != 1 && stride != 2) || C > 2048) {
     vpb_set_error("depthwise: unsupported C=%d k=%d stride=%d", C, k, stride);
     return VPB_ERR_ARG;
@@ -507,9 +512,9 @@ int vpb::depthwise_x(int dtype, const void* in, const void* in_lo, int H, int W,
 #define DW_LAUNCH(E, K, S)                                                                             \
   do {                                                                                                 \
     if (sp) VPB_CUDA_OK(launch_k(depthwise_kernel<E, K, S, true>, dim3(g.nblocks), dim3(g.threads), smem, st, i4, i4l, H, W, C, \
-                                 w, bias, o4, o4l, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block));  \
+                                 w, bias, o4, o4l, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block, act));  \
     else VPB_CUDA_OK(launch_k(depthwise_kernel<E, K, S, false>, dim3(g.nblocks), dim3(g.threads), smem, st, i4, i4l, H, W, C, \
-                              w, bias, o4, o4l, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block));     \
+                              w, bias, o4, o4l, g.Ho, g.Wo, gap_acc, g.G, g.PPB, g.pix_per_block, act));     \
   } while (0)
 #define DW_DISPATCH(E)                                            \
   do {                                                            \
@@ -567,12 +572,12 @@ extern "C" int vpb_ctx_conv1(int dtype, const float* in, int H, int W, const flo
   return vpb::ctx_conv1_x(dtype, in, H, W, w, b, Cout, out, nullptr, out_pad, static_cast<cudaStream_t>(stream));
 }
 int vpb::ctx_conv1_x(int dtype, const float* in, int H, int W, const float* w, const float* b, int Cout, void* out,
-                     void* out_lo, int out_pad, cudaStream_t st) {
+                     void* out_lo, int out_pad, cudaStream_t st, int act) {
   const int n = H * W * Cout;
   if (dtype == VPB_BF16)
-    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<BF16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), out_pad));
+    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<BF16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), out_pad, act));
   else
-    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<F16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__half*>(out), static_cast<__half*>(out_lo), out_pad));
+    VPB_CUDA_OK(launch_k(ctx_conv1_kernel<F16>, dim3((n + 255) / 256), dim3(256), 0, st, in, H, W, w, b, Cout, static_cast<__half*>(out), static_cast<__half*>(out_lo), out_pad, act));
   return VPB_OK;
 }
 

@@ -12,6 +12,7 @@
 #include "conv_gemm.cuh"
 #include "ops_internal.h"
 #include "../../include/vp_b200.h"
+#include "engine_internal.h"
 
 #include <cmath>
 #include <cstdio>
@@ -29,14 +30,7 @@ namespace vpb {
 // magic "VPW1", u32 n; per tensor: u32 name_len, name, u32 dtype (0 f32, 1 i64), u32 ndim,
 // u32 dims[ndim], u64 nbytes, raw little-endian data.  Written by
 // autoware_vision_pilot_b200/weights.py from the reference's .pth state_dict.
-struct HostTensor {
-  std::vector<int> dims;
-  std::vector<float> f;
-  size_t numel() const { size_t n = 1; for (int d : dims) n *= d; return n; }
-};
-using WeightMap = std::map<std::string, HostTensor>;
-
-static int load_vpw(const char* path, WeightMap& out) {
+int load_vpw(const char* path, WeightMap& out) {
   FILE* fp = fopen(path, "rb");
   if (!fp) { vpb_set_error("cannot open weight file '%s'", path); return VPB_ERR_IO; }
   auto fail = [&](const char* why) { fclose(fp); vpb_set_error("%s: %s", path, why); return VPB_ERR_IO; };
@@ -133,13 +127,7 @@ static Prefixes prefixes_for(int kind) {
 
 using namespace vpb;
 
-// RAII: make the engine's device current for the duration of a C-ABI call and restore the caller's
-// device afterwards (several engines / threads / GPUs may share one process).
-struct DeviceGuard {
-  int prev = -1; bool changed = false;
-  explicit DeviceGuard(int d) { if (cudaGetDevice(&prev) == cudaSuccess && prev != d) changed = cudaSetDevice(d) == cudaSuccess; }
-  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
-};
+using vpb::DeviceGuard;
 
 struct vp_engine {
   vp_engine_config cfg{};
@@ -307,7 +295,7 @@ namespace vpb {
   auto it_##__LINE__ = (w).find(key);                                            \
   if (it_##__LINE__ == (w).end()) { vpb_set_error("weight '%s' missing", std::string(key).c_str()); return VPB_ERR_IO; }
 
-static const HostTensor* find_w(const WeightMap& w, const std::string& key) {
+const HostTensor* find_w(const WeightMap& w, const std::string& key) {
   auto it = w.find(key);
   if (it == w.end()) { vpb_set_error("weight '%s' missing from checkpoint", key.c_str()); return nullptr; }
   return &it->second;
@@ -315,7 +303,7 @@ static const HostTensor* find_w(const WeightMap& w, const std::string& key) {
 
 // Every tensor's shape is checked against what the architecture expects before it is indexed: a checkpoint
 // of another variant, or a truncated / corrupt file, fails with VPB_ERR_IO instead of reading out of bounds.
-static const HostTensor* find_w_shaped(const WeightMap& w, const std::string& key, std::initializer_list<int> dims) {
+const HostTensor* find_w_shaped(const WeightMap& w, const std::string& key, std::initializer_list<int> dims) {
   const HostTensor* t = find_w(w, key);
   if (!t) return nullptr;
   bool ok = t->dims.size() == dims.size() && t->f.size() == t->numel();
@@ -344,7 +332,7 @@ static bool bn_fold(const WeightMap& w, const std::string& p, int C, std::vector
 }
 
 // Conv2d weight [Cout][Cin][k][k] -> [k*k][Cout][Cin] (optionally scaled per Cout)
-static std::vector<float> pack_conv(const HostTensor& t, const std::vector<float>* scale) {
+std::vector<float> pack_conv(const HostTensor& t, const std::vector<float>* scale) {
   const int Cout = t.dims[0], Cin = t.dims[1], k = t.dims[2];
   std::vector<float> o(t.f.size());
   for (int co = 0; co < Cout; ++co)

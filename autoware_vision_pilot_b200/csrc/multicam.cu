@@ -10,6 +10,7 @@
 // NCCL is resolved with dlopen at first use so that the library has no link-time NCCL dependency.
 #include "common.cuh"
 #include "ops_internal.h"
+#include "engine_internal.h"
 #include "../../include/vp_b200_multicam.h"
 
 #include <dlfcn.h>
@@ -114,11 +115,6 @@ __global__ void multicam_reset_kernel(double* state) {
   if (i == 0) { state[24] = 4.0; state[25] = 0.5 * 0.5; }     // lane width slot, path_finder.cpp:41-43
 }
 
-struct DeviceGuard {   // RAII: run the body on device `d`, restore the caller's device afterwards
-  int prev = -1; bool changed = false;
-  explicit DeviceGuard(int d) { if (cudaGetDevice(&prev) == cudaSuccess && prev != d) changed = cudaSetDevice(d) == cudaSuccess; }
-  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
-};
 
 }  // namespace vpb
 

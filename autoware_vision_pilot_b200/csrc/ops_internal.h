@@ -23,6 +23,9 @@ struct PreprocessPlan {
   int TY = 20, pitch = 0, xt = 16;   // Pillow kernel: output rows per block, smem row pitch (bytes), tap capacity (16 | 32)
   int device = -1;                   // device that owns d_tables
   void* out_lo = nullptr;            // split-fp16 mode: low half of the output tensor (set once by the engine)
+  // output canvas (letterbox, auto_speed_infer.py:24-45): the OW x OH resized image is pasted at (out_x0, out_y0) of a
+  // canvas with out_pitch pixels per row (0 = OW) and out_c channels per pixel (4 | 8)
+  int out_pitch = 0, out_x0 = 0, out_y0 = 0, out_c = 4;
   size_t smem_bytes = 0;
   int* d_tables = nullptr;
   size_t off_xb = 0, off_xk = 0, off_yb = 0, off_yk = 0;
@@ -46,13 +49,13 @@ DwGeom dw_geometry(int H, int W, int C, int k, int stride);
 int stem_conv_x(int dtype, const void* in, const void* in_lo, int H, int W, const float* w, const float* bias,
                 void* out, void* out_lo, cudaStream_t st);
 int depthwise_x(int dtype, const void* in, const void* in_lo, int H, int W, int C, int k, int stride, const float* w,
-                const float* bias, void* out, void* out_lo, long long* gap_acc, cudaStream_t st);
+                const float* bias, void* out, void* out_lo, long long* gap_acc, cudaStream_t st, int act = 1 /* SiLU; 0 = none */);
 int se_scale_x(int dtype, const long long* gap_acc, int HW, int C, int sq, const float* w1, const float* b1,
                const float* w2, const float* b2, const float* w_proj, int Cout, void* w_scaled, void* w_scaled_lo,
                float* scale_out, cudaStream_t st);
 int gap_x(int dtype, const void* in, const void* in_lo, int HW, int C, int ld, float* out, cudaStream_t st);
 int ctx_conv1_x(int dtype, const float* in, int H, int W, const float* w, const float* b, int Cout, void* out,
-                void* out_lo, int out_pad, cudaStream_t st);
+                void* out_lo, int out_pad, cudaStream_t st, int act = 1 /* ACT_GELU; 2 = ACT_SILU */);
 int fuse_pool_x(int dtype, const void* f0, const void* f1, const void* f2, const void* f3, const void* f4,
                 const size_t lo_off[5], int H4, int W4, void* out, void* out_lo, cudaStream_t st);
 

@@ -25,6 +25,10 @@
 namespace vpb {
 
 // ---------------------------------------------------------------- host: coefficient tables
+static double bilinear_filter(double x) {     // Pillow Resample.c bilinear_filter (triangle), support 1.0
+  if (x < 0.0) x = -x;
+  return x < 1.0 ? 1.0 - x : 0.0;
+}
 static double bicubic_filter(double x) {
   const double a = -0.5;
   if (x < 0.0) x = -x;
@@ -35,10 +39,10 @@ static double bicubic_filter(double x) {
 
 // Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc (BICUBIC, support 2.0).
 static void pil_axis(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& coeffs,
-                     int& ksize) {
+                     int& ksize, bool bilinear = false) {
   const double scale = static_cast<double>(in_size) / out_size;
   const double filterscale = scale < 1.0 ? 1.0 : scale;
-  const double support = 2.0 * filterscale;
+  const double support = (bilinear ? 1.0 : 2.0) * filterscale;
   ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
   bounds.assign(out_size, 0);
   coeffs.assign(static_cast<size_t>(out_size) * ksize, 0);
@@ -53,7 +57,7 @@ static void pil_axis(int in_size, int out_size, std::vector<int>& bounds, std::v
     xmax -= xmin;
     double ww = 0.0;
     for (int x = 0; x < xmax; ++x) {
-      const double w = bicubic_filter((x + xmin - center + 0.5) * ss);
+      const double w = bilinear ? bilinear_filter((x + xmin - center + 0.5) * ss) : bicubic_filter((x + xmin - center + 0.5) * ss);
       k[x] = w;
       ww += w;
     }
@@ -87,9 +91,12 @@ static void cv_axis(int in_size, int out_size, std::vector<int>& bounds, std::ve
   }
 }
 
+static inline bool is_pil(int mode) { return mode == VPB_RESIZE_PIL_BICUBIC || mode == VPB_RESIZE_PIL_BILINEAR; }
+
 void resize_tables_host(int mode, int in_size, int out_size, std::vector<int>& bounds,
                         std::vector<int>& coeffs, int& ksize) {
   if (mode == VPB_RESIZE_PIL_BICUBIC) pil_axis(in_size, out_size, bounds, coeffs, ksize);
+  else if (mode == VPB_RESIZE_PIL_BILINEAR) pil_axis(in_size, out_size, bounds, coeffs, ksize, true);
   else cv_axis(in_size, out_size, bounds, coeffs, ksize);
 }
 
@@ -105,6 +112,7 @@ struct PreParams {
   const int* yb; const int* yk; int yks;   // vertical
   void* out;            // [OH][OW][4] 16-bit
   void* out_lo;         // split-fp16 mode: low half of the normalised tensor (NULL otherwise)
+  int out_pitch, out_x0, out_y0, out_c;   // output canvas: pixels per row, paste offset, channels per pixel (4 | 8)
   uint8_t* out_u8;      // optional [OH][OW][3] resized image in tensor channel order
   int OH, OW;
 };
@@ -123,8 +131,9 @@ __device__ __forceinline__ void emit_pixel(const PreParams& p, int oy, int ox, c
   uint2 o, l;
   split2<E>(v[0], v[1], o.x, l.x);
   split2<E>(v[2], 0.f, o.y, l.y);
-  reinterpret_cast<uint2*>(p.out)[static_cast<size_t>(oy) * p.OW + ox] = o;
-  if (p.out_lo) reinterpret_cast<uint2*>(p.out_lo)[static_cast<size_t>(oy) * p.OW + ox] = l;
+  const size_t pix = static_cast<size_t>(oy + p.out_y0) * p.out_pitch + (ox + p.out_x0);
+  reinterpret_cast<uint2*>(p.out)[pix * (p.out_c >> 2)] = o;
+  if (p.out_lo) reinterpret_cast<uint2*>(p.out_lo)[pix * (p.out_c >> 2)] = l;
 }
 
 static constexpr int kTX = 32;                // output columns per block (96 output bytes per row)
@@ -236,17 +245,18 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_pil_kernel(const PrePa
       const float mean = tc == 0 ? p.mean[0] : tc == 1 ? p.mean[1] : p.mean[2];     // selects, not a dynamic
       const float stdv = tc == 0 ? p.stdv[0] : tc == 1 ? p.stdv[1] : p.stdv[2];     // index into the params
       const float v = __fdiv_rn(x - mean, stdv);
-      const size_t pix = static_cast<size_t>(oy) * p.OW + ox;
+      const size_t pix = static_cast<size_t>(oy + p.out_y0) * p.out_pitch + (ox + p.out_x0);
+      const size_t ei = pix * p.out_c + tc;                  // element index (out_c is even: ei is even for tc == 2)
       const typename E::T hi = from_f32<E>(v);
-      if (tc == 2) reinterpret_cast<uint32_t*>(outp)[pix * 2 + 1] = pack2<E>(v, 0.f);   // (channel 2, zero pad)
-      else outp[pix * 4 + tc] = hi;
+      if (tc == 2) reinterpret_cast<uint32_t*>(outp)[ei >> 1] = pack2<E>(v, 0.f);   // (channel 2, zero pad)
+      else outp[ei] = hi;
       if (p.out_lo) {
         typename E::T* lop = reinterpret_cast<typename E::T*>(p.out_lo);
         const float lo = v - to_f32<E>(hi);
-        if (tc == 2) reinterpret_cast<uint32_t*>(lop)[pix * 2 + 1] = pack2<E>(lo, 0.f);
-        else lop[pix * 4 + tc] = from_f32<E>(lo);
+        if (tc == 2) reinterpret_cast<uint32_t*>(lop)[ei >> 1] = pack2<E>(lo, 0.f);
+        else lop[ei] = from_f32<E>(lo);
       }
-      if (p.out_u8) p.out_u8[pix * 3 + tc] = static_cast<uint8_t>(u[b]);
+      if (p.out_u8) p.out_u8[(static_cast<size_t>(oy) * p.OW + ox) * 3 + tc] = static_cast<uint8_t>(u[b]);
     }
   }
 }
@@ -303,11 +313,11 @@ int PreprocessPlan::configure(int in_h, int in_w, int mode_) {
     resize_tables_host(mode, w, OW, xb, xk, xks);
     resize_tables_host(mode, h, OH, yb, yk, yks);
   }
-  if (mode == VPB_RESIZE_PIL_BICUBIC && (xks > 32 || yks > 32)) {
+  if (is_pil(mode) && (xks > 32 || yks > 32)) {
     vpb_set_error("preprocess: %dx%d -> %dx%d needs %d-tap filters (max 32: input at most ~7x the network size)", w, h, OW, OH, std::max(xks, yks));
     return VPB_ERR_ARG;
   }
-  if (mode == VPB_RESIZE_PIL_BICUBIC) {
+  if (is_pil(mode)) {
     // worst-case tile extents for the shared-memory staging; the row tile TY shrinks until two blocks fit an SM
     // (very large inputs: until one does)
     patch_w_cap = 0;
@@ -360,15 +370,17 @@ PreprocessPlan::~PreprocessPlan() {
 static void fill_params(const PreprocessPlan& pl, const uint8_t* src, int stride, int convention,
                         void* out, uint8_t* out_u8, PreParams& p) {
   p.out_lo = pl.out_lo;
+  p.out_pitch = pl.out_pitch > 0 ? pl.out_pitch : pl.OW; p.out_x0 = pl.out_x0; p.out_y0 = pl.out_y0;
+  p.out_c = pl.out_c;
   p.src = src; p.h = pl.h; p.w = pl.w; p.stride = stride; p.mode = pl.mode;
   // conventions: see include/vp_b200_ops.h
   static const float kMeanRGB[3] = {0.485f, 0.456f, 0.406f}, kStdRGB[3] = {0.229f, 0.224f, 0.225f};
   p.swap_rb = convention == VPB_CONV_BGR_SWAP ? 1 : 0;
-  p.mul_inv255 = convention == VPB_CONV_RGB ? 0 : 1;
+  p.mul_inv255 = (convention == VPB_CONV_RGB || convention == VPB_CONV_RGB_UNIT) ? 0 : 1;
   for (int c = 0; c < 3; ++c) {
     const int s = convention == VPB_CONV_BGR_NOSWAP ? 2 - c : c;   // BGR-ordered stats (tensorrt_backend.cpp:167-168)
-    p.mean[c] = kMeanRGB[s];
-    p.stdv[c] = kStdRGB[s];
+    p.mean[c] = convention == VPB_CONV_RGB_UNIT ? 0.f : kMeanRGB[s];   // ToTensor only (auto_speed_infer.py:50)
+    p.stdv[c] = convention == VPB_CONV_RGB_UNIT ? 1.f : kStdRGB[s];
   }
   p.xb = pl.d_tables + pl.off_xb; p.xk = pl.d_tables + pl.off_xk; p.xks = pl.xks;
   p.yb = pl.d_tables + pl.off_yb; p.yk = pl.d_tables + pl.off_yk; p.yks = pl.yks;
@@ -376,7 +388,7 @@ static void fill_params(const PreprocessPlan& pl, const uint8_t* src, int stride
 }
 
 static const void* kernel_func(int mode, int dtype, int xt) {
-  if (mode == VPB_RESIZE_PIL_BICUBIC) {
+  if (is_pil(mode)) {
     if (xt == 16)
       return dtype == VPB_BF16 ? reinterpret_cast<const void*>(preprocess_pil_kernel<BF16, 16>)
                                : reinterpret_cast<const void*>(preprocess_pil_kernel<F16, 16>);
@@ -402,7 +414,7 @@ int PreprocessPlan::update_graph_node(cudaGraphExec_t exec, cudaGraphNode_t node
   kp.func = const_cast<void*>(kernel_func(mode, dtype, xt));
   kp.kernelParams = args;
   kp.extra = nullptr;
-  if (mode == VPB_RESIZE_PIL_BICUBIC) {
+  if (is_pil(mode)) {
     kp.gridDim = dim3((OW + kTX - 1) / kTX, (OH + TY - 1) / TY);
     kp.blockDim = dim3(kPreThreads);
     kp.sharedMemBytes = static_cast<unsigned>(smem_bytes);
@@ -419,7 +431,7 @@ int PreprocessPlan::launch(const uint8_t* src, int stride, int convention, int d
                            uint8_t* out_u8, cudaStream_t stream) const {
   PreParams p;
   fill_params(*this, src, stride, convention, out, out_u8, p);
-  if (mode == VPB_RESIZE_PIL_BICUBIC) {
+  if (is_pil(mode)) {
     dim3 grid((OW + kTX - 1) / kTX, (OH + TY - 1) / TY);
     {
       std::lock_guard<std::mutex> g(init_mutex());
@@ -454,7 +466,7 @@ int PreprocessPlan::launch(const uint8_t* src, int stride, int convention, int d
 extern "C" int vpb_resize_tables_host(int mode, int in_size, int out_size, int* bounds, int* coeffs,
                                       int coeffs_cap, int* ksize) {
   if (!bounds || !coeffs || !ksize || in_size <= 0 || out_size <= 0 ||
-      (mode != VPB_RESIZE_PIL_BICUBIC && mode != VPB_RESIZE_CV_LINEAR)) {
+      (mode != VPB_RESIZE_PIL_BICUBIC && mode != VPB_RESIZE_CV_LINEAR && mode != VPB_RESIZE_PIL_BILINEAR)) {
     vpb_set_error("vpb_resize_tables_host: bad arguments");
     return VPB_ERR_ARG;
   }

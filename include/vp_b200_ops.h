@@ -23,7 +23,7 @@ extern "C" {
 
 enum { VPB_OK = 0, VPB_ERR_ARG = -1, VPB_ERR_CUDA = -2, VPB_ERR_STATE = -3, VPB_ERR_IO = -4 };
 enum { VPB_F16 = 0, VPB_BF16 = 1 };
-enum { VPB_ACT_NONE = 0, VPB_ACT_GELU = 1, VPB_ACT_SILU = 2, VPB_ACT_SIGMOID = 3 };
+enum { VPB_ACT_NONE = 0, VPB_ACT_GELU = 1, VPB_ACT_SILU = 2, VPB_ACT_SIGMOID = 3, VPB_ACT_SILU2 = 4 /* SiLU(SiLU(x)) */ };
 /* conv epilogue modes */
 enum {
   VPB_EPI_STORE = 0,  /* out = act(acc + bias)                                   */
@@ -99,6 +99,20 @@ typedef struct {
    * fp32 TMEM accumulator (the dropped A_lo*W_lo term is 2^-22 relative) and the epilogue writes (out, out_lo).
    * All *_lo tensors have exactly the layout of their hi partner; res_lo / in2_lo / w2_lo are required iff the hi
    * partner is given. */
+  /* Widening for the AutoSpeed detector, TILE algorithm:
+   *   stride   1 (default when 0) or 2: Conv2d 3x3 / 1x1 with stride 2, padding 1 (common_layers.py:8 with s=2);
+   *            H, W are the OUTPUT size, in_h x in_w the input size (0 = H x W); the input is sampled through the
+   *            tensor map's traversal stride, zero padding stays the TMA unit's out-of-bounds fill;
+   *   ldw      elements between consecutive output-channel rows of w (0 = Cin): lets a [tokens][channels] activation
+   *            slice act as the weight matrix (attention: S = Q K^T, O = P V^T as 1x1 "convolutions");
+   *   act2     activation applied AFTER the residual step of modes ADD / MULADD (CTX block: SiLU(SiLU(conv) * x + x),
+   *            common_layers.py:226-232); VPB_ACT_NONE = off. */
+  int stride, in_h, in_w;
+  int ldw;
+  int act2;
+  int out_slice;          /* 1: out (and res) point at a channel SLICE of a wider tensor (concat without a copy:
+                             torch.cat in C3K2 / SPPF / the necks, common_layers.py:191,254): only round8(Cout) channels
+                             of each ldo-wide row are written; 0: the whole ldo-wide row belongs to this layer */
   const void* in_lo;
   const void* w_lo;
   void* out_lo;
@@ -119,8 +133,10 @@ int vpb_conv_gemm(const vpb_conv_args* a, void* stream);
  *               x*(1/255)                                                  (tensorrt_backend.cpp:160-177)
  *   BGR_SWAP    EgoLanes C++ engine: BGR in -> RGB, RGB stats, x*(1/255)   (tensorrt_engine.cpp:190-220)
  * out_u8 (optional): the resized uint8 image [320][640][3] in tensor channel order. */
-enum { VPB_RESIZE_NONE = 0, VPB_RESIZE_PIL_BICUBIC = 1, VPB_RESIZE_CV_LINEAR = 2 };
-enum { VPB_CONV_RGB = 0, VPB_CONV_BGR_NOSWAP = 1, VPB_CONV_BGR_SWAP = 2 };
+enum { VPB_RESIZE_NONE = 0, VPB_RESIZE_PIL_BICUBIC = 1, VPB_RESIZE_CV_LINEAR = 2,
+       VPB_RESIZE_PIL_BILINEAR = 3 /* Pillow Image.BILINEAR with antialias: the AutoSpeed letterbox, auto_speed_infer.py:38 */ };
+enum { VPB_CONV_RGB = 0, VPB_CONV_BGR_NOSWAP = 1, VPB_CONV_BGR_SWAP = 2,
+       VPB_CONV_RGB_UNIT = 3 /* RGB in, x/255 only (transforms.ToTensor, auto_speed_infer.py:50) */ };
 int vpb_preprocess(const uint8_t* src_dev, int h, int w, int stride, int resize_mode, int convention,
                    int dtype, void* out_dev, uint8_t* out_u8_dev, void* stream);
 /* Host-only: the integer coefficient tables the kernel uses (bounds[out_size],

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for h in ("vp_b200.h", "vp_b200_ops.h", "vp_b200_multicam.h"):
+    for h in ("vp_b200.h", "vp_b200_ops.h", "vp_b200_multicam.h", "vp_b200_autospeed.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(vpb?_[a-z0-9_]+)\s*\(", src))
@@ -178,3 +178,37 @@ def test_ctypes_mirrors_match_the_c_struct_layouts(tmp_path):
         assert int(out[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_pillow_bilinear_tables_reproduce_pillow(tmp_path):
+    """AutoSpeed letterbox (auto_speed_infer.py:38): the C++ coefficient tables for Pillow's BILINEAR (antialias) filter,
+    run through the kernel's integer arithmetic in numpy, reproduce Image.resize(BILINEAR) bit for bit."""
+    from PIL import Image
+    lib = L.lib()
+    lib.vpb_resize_tables_host.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                           C.c_int, C.POINTER(C.c_int)]
+
+    def tables(in_size, out_size):
+        bounds = (C.c_int * out_size)()
+        coeffs = (C.c_int * (out_size * 64))()
+        ks = C.c_int()
+        L.check(lib.vpb_resize_tables_host(3, in_size, out_size, bounds, coeffs, out_size * 64, C.byref(ks)), "tables")
+        return (np.frombuffer(bounds, dtype=np.int32).copy(),
+                np.frombuffer(coeffs, dtype=np.int32)[: out_size * ks.value].reshape(out_size, ks.value).copy())
+
+    rng = np.random.default_rng(4)
+    for (h, w, oh, ow) in ((270, 480, 128, 227), (100, 130, 256, 333)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        xb, xk = tables(w, ow)
+        yb, yk = tables(h, oh)
+
+        def axis_pass(a, b, k, n_in):            # a [rows, n_in, 3] -> [rows, len(b), 3]
+            out = np.zeros((a.shape[0], len(b), 3), np.int64)
+            for o in range(len(b)):
+                n = min(k.shape[1], n_in - b[o])
+                out[:, o] = (a[:, b[o]:b[o] + n].astype(np.int64) * k[o, :n, None]).sum(1)
+            return np.clip((out + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+
+        hor = axis_pass(img, xb, xk, w)
+        ver = axis_pass(hor.transpose(1, 0, 2), yb, yk, h).transpose(1, 0, 2)
+        assert np.array_equal(ver, np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR)))
