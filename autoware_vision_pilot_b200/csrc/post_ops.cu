@@ -344,3 +344,40 @@ extern "C" int vpb_bayes_fuse(double* state, const double* meas, int n_meas, voi
   VPB_CUDA_OK(cudaGetLastError());
   return VPB_OK;
 }
+
+// ---------------------------------------------------------------------------- AutoSteer boundary
+// The production AutoSteer network is an ONNX file whose graph and weights are NOT in the reference repository
+// (production_release/README.md:112); what the reference does define around it is built here, on the device:
+//   * the temporal input buffer: concat(EgoLanes raw tensor at t-1, at t) -> [1, 6, 80, 160]
+//     (main.cpp:515-534, boost::circular_buffer of two 38 400-float tensors; first frame: no inference);
+//   * the post-process: argmax over the 61 logits of the SECOND output, steering = argmax - 30 degrees
+//     (autosteer_engine.cpp:157-187: strict >, first maximum wins).
+namespace vpb {
+__global__ void autosteer_pack_kernel(const float* __restrict__ cur, float* __restrict__ buf, int n, int* __restrict__ filled) {
+  // buf = [t-1 | t]; shift t -> t-1, copy cur -> t; *filled counts frames seen (saturates at 2)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float old = buf[n + i]; buf[i] = old; buf[n + i] = cur[i]; }
+  if (i == 0) *filled = min(*filled + 1, 2);
+}
+__global__ void autosteer_decode_kernel(const float* __restrict__ logits, int n, float* __restrict__ angle, int* __restrict__ cls) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int best = 0; float bv = logits[0];
+  for (int i = 1; i < n; ++i) if (logits[i] > bv) { bv = logits[i]; best = i; }
+  *cls = best;
+  *angle = static_cast<float>(best - 30);
+}
+}  // namespace vpb
+
+extern "C" int vpb_autosteer_pack(const float* egolanes_raw_dev, float* buffer_dev, int* filled_dev, void* stream) {
+  if (!egolanes_raw_dev || !buffer_dev || !filled_dev) { vpb_set_error("vpb_autosteer_pack: null argument"); return VPB_ERR_ARG; }
+  const int n = 3 * 80 * 160;
+  vpb::autosteer_pack_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(egolanes_raw_dev, buffer_dev, n, filled_dev);
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}
+extern "C" int vpb_autosteer_decode(const float* logits_dev, int n_classes, float* angle_deg_dev, int* class_dev, void* stream) {
+  if (!logits_dev || !angle_deg_dev || !class_dev || n_classes < 1) { vpb_set_error("vpb_autosteer_decode: bad argument"); return VPB_ERR_ARG; }
+  vpb::autosteer_decode_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(logits_dev, n_classes, angle_deg_dev, class_dev);
+  VPB_CUDA_OK(cudaGetLastError());
+  return VPB_OK;
+}

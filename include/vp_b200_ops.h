@@ -268,6 +268,17 @@ int vpb_lateral_update(const float* masks, int H, int W, int img_w, int img_h, f
                        const double* homography, double autosteer_steering_rad,
                        vpb_lateral_state* state_dev, vpb_lateral_out* out_dev, void* stream);
 
+/* ---- AutoSteer boundary ----
+ * The AutoSteer v1 network itself (ONNX [1,6,80,160] -> 2 x [1,61]) is not in the reference repository
+ * (production_release/README.md:112), so only the defined pieces around it exist here, device-resident:
+ *   vpb_autosteer_pack    main.cpp:515-534: the two-frame circular buffer; buffer_dev is float [2][3*80*160] = the network
+ *                         input [1,6,80,160] (t-1 then t); *filled_dev = frames seen so far, saturating at 2 (the reference
+ *                         skips inference until the buffer is full);
+ *   vpb_autosteer_decode  AutoSteerOnnxEngine::postProcess autosteer_engine.cpp:157-187: class = first argmax of the
+ *                         n_classes (61) logits of the second output, steering angle = class - 30 degrees. */
+int vpb_autosteer_pack(const float* egolanes_raw_dev, float* buffer_dev, int* filled_dev, void* stream);
+int vpb_autosteer_decode(const float* logits_dev, int n_classes, float* angle_deg_dev, int* class_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,3 +144,35 @@ def test_visualize_mask_overlay_is_bit_exact(viz, code, h, w):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), post.visualize_mask(mask, frame, viz))
     assert lib.vpb_visualize_mask(dm.data_ptr(), 320, 640, 7, df.data_ptr(), h, w, 3 * w, out.data_ptr(), 3 * w, None) != 0
+
+
+def test_autosteer_buffer_and_decode():
+    """The defined pieces of the AutoSteer boundary (the network graph is not in the reference repo): two-frame input
+    buffer (main.cpp:515-534) and argmax - 30 (autosteer_engine.cpp:157-187), device-resident."""
+    import ctypes as C
+    from autoware_vision_pilot_b200 import _lib as L
+    lib = L.lib()
+    lib.vpb_autosteer_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vpb_autosteer_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = 3 * 80 * 160
+    buf = torch.zeros(2, n, device="cuda")
+    filled = torch.zeros(1, dtype=torch.int32, device="cuda")
+    frames = [torch.randn(n, device="cuda") for _ in range(3)]
+    for k, f in enumerate(frames):
+        L.check(lib.vpb_autosteer_pack(f.data_ptr(), buf.data_ptr(), filled.data_ptr(), None), "pack")
+        torch.cuda.synchronize()
+        assert filled.item() == min(k + 1, 2)
+        assert torch.equal(buf[1], f)
+        if k:
+            assert torch.equal(buf[0], frames[k - 1])                 # [t-1 | t] == the reference's concat order
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        lg = rng.normal(size=61).astype(np.float32)
+        if _ % 4 == 0:
+            lg[[7, 40]] = lg.max() + 1.0                              # tie: the first maximum wins (strict >)
+        t = torch.from_numpy(lg).cuda()
+        ang = torch.zeros(1, device="cuda")
+        cls = torch.zeros(1, dtype=torch.int32, device="cuda")
+        L.check(lib.vpb_autosteer_decode(t.data_ptr(), 61, ang.data_ptr(), cls.data_ptr(), None), "decode")
+        torch.cuda.synchronize()
+        assert cls.item() == int(np.argmax(lg)) and ang.item() == float(np.argmax(lg) - 30)
