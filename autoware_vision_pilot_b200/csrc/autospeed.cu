@@ -348,6 +348,7 @@ struct vp_autospeed {
   static constexpr int kMaxCand = 4096, kMaxDet = 1024;
   cudaGraphExec_t gexec = nullptr; cudaGraph_t graph = nullptr;
   const uint8_t* g_src = nullptr; int g_stride = 0;
+  cudaGraphNode_t g_pre_node = nullptr;      // the captured letterbox kernel node (re-pointed per frame)
 
   ~vp_autospeed() {
     DeviceGuard g(gpu_id);
@@ -758,8 +759,15 @@ static int as_configure(vp_autospeed& e, int h, int w) {
 static int as_enqueue(vp_autospeed& e, const uint8_t* src, int h, int w, int stride) {
   int rc = as_configure(e, h, w);
   if (rc) return rc;
+  if (e.gexec && e.g_stride == stride && e.g_src != src && e.g_pre_node) {
+    // same geometry, another frame buffer: re-point the letterbox node instead of re-capturing
+    rc = e.pre.update_graph_node(e.gexec, e.g_pre_node, src, stride, VPB_CONV_RGB_UNIT, e.dtype, e.d_canvas, nullptr);
+    if (rc) return rc;
+    e.g_src = src;
+  }
   if (!e.gexec || e.g_src != src || e.g_stride != stride) {
     if (e.gexec) { cudaGraphExecDestroy(e.gexec); e.gexec = nullptr; }
+    e.g_pre_node = nullptr;
     rc = as_launch_all(e, src, stride, e.stream);             // warm (function attributes) + correct results
     if (rc) return rc;
     VPB_CUDA_OK(cudaStreamSynchronize(e.stream));
@@ -769,6 +777,18 @@ static int as_enqueue(vp_autospeed& e, const uint8_t* src, int h, int w, int str
     const cudaError_t ce = cudaStreamEndCapture(e.stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (ce != cudaSuccess) { vpb_set_error("autospeed: graph capture failed: %s", cudaGetErrorString(ce)); return VPB_ERR_CUDA; }
+    {
+      size_t nn = 0;
+      cudaGraphGetNodes(g, nullptr, &nn);
+      std::vector<cudaGraphNode_t> nodes(nn);
+      cudaGraphGetNodes(g, nodes.data(), &nn);
+      for (size_t i = 0; i < nn; ++i) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp{};
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && e.pre.owns_kernel(kp.func, e.dtype)) { e.g_pre_node = nodes[i]; break; }
+      }
+    }
     const cudaError_t ci = cudaGraphInstantiate(&e.gexec, g, 0);
     if (e.graph) cudaGraphDestroy(e.graph);
     e.graph = g;
