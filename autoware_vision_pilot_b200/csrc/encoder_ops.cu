@@ -203,7 +203,12 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const uint4* __restrict_
 }
 
 // ------------------------------------------------------------------ squeeze-excitation gate
-// Every block recomputes the (tiny) gate, then scales its slice of the projection weights.
+// Every block recomputes the (tiny) gate, then scales its slice of the depthwise OUTPUT in place (x <- x * gate[c]),
+// exactly where the reference graph applies it (torchvision SqueezeExcitation: `scale * input`).
+// Round 1 folded the gate into the 16-bit projection weights instead (w <- fp16(w * gate)), saving this pass over the
+// activations; the wider parity set of round 2 showed that variant 3-8x less accurate on frames other than the
+// calibration frame (f4: 0.13-0.35 sigma vs 0.04-0.07 sigma; reproduced bit-for-bit by a CPU emulation of the fp16
+// storage, profiles/r2_se_gate_precision.md), so the gate is back on the activation side.
 // The kernel is a chain of four dependent phases, each bound by one L2 round trip, so every phase
 // issues all of its loads before consuming them (float4 rows, unrolled loops).
 template <class E>
@@ -213,9 +218,7 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
                                                         const float* __restrict__ b1,
                                                         const float* __restrict__ w2t,
                                                         const float* __restrict__ b2,
-                                                        const float* __restrict__ w_proj, int Cout,
-                                                        typename E::T* __restrict__ w_scaled,
-                                                        typename E::T* __restrict__ w_scaled_lo,
+                                                        uint4* __restrict__ act, uint4* __restrict__ act_lo, int n8,
                                                         float* __restrict__ scale_out) {
   pdl_launch_dependents();
   pdl_wait();
@@ -279,18 +282,21 @@ __global__ void __launch_bounds__(512) se_scale_kernel(const long long* __restri
     if (scale_out && blockIdx.x == 0) scale_out[c] = g;
   }
   __syncthreads();
-  // scaled projection weights, 8 elements (one 16-byte store) per thread-iteration
-  const int C8 = C >> 3, total8 = Cout * C8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += gridDim.x * blockDim.x) {
-    const int k8 = (i % C8) * 8;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(w_proj) + 2 * i);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(w_proj) + 2 * i + 1);
-    const float* g = gate + k8;
+  // gated activations in place, 8 channels (one 16-byte load / store) per thread-iteration; n8 = HW * C / 8
+  const int C8 = C >> 3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += gridDim.x * blockDim.x) {
+    const float* g = gate + (i % C8) * 8;
+    const uint4 v = act[i];
+    float2 a = unpack2<E>(v.x), b = unpack2<E>(v.y), c = unpack2<E>(v.z), d = unpack2<E>(v.w);
+    if (act_lo) {
+      const uint4 vl = act_lo[i];
+      a = join2<E>(v.x, vl.x); b = join2<E>(v.y, vl.y); c = join2<E>(v.z, vl.z); d = join2<E>(v.w, vl.w);
+    }
     uint4 o, l;
-    split2<E>(a.x * g[0], a.y * g[1], o.x, l.x); split2<E>(a.z * g[2], a.w * g[3], o.y, l.y);
-    split2<E>(b.x * g[4], b.y * g[5], o.z, l.z); split2<E>(b.z * g[6], b.w * g[7], o.w, l.w);
-    reinterpret_cast<uint4*>(w_scaled)[i] = o;
-    if (w_scaled_lo) reinterpret_cast<uint4*>(w_scaled_lo)[i] = l;
+    split2<E>(a.x * g[0], a.y * g[1], o.x, l.x); split2<E>(b.x * g[2], b.y * g[3], o.y, l.y);
+    split2<E>(c.x * g[4], c.y * g[5], o.z, l.z); split2<E>(d.x * g[6], d.y * g[7], o.w, l.w);
+    act[i] = o;
+    if (act_lo) act_lo[i] = l;
   }
 }
 
@@ -531,22 +537,23 @@ int vpb::depthwise_x(int dtype, const void* in, const void* in_lo, int H, int W,
 
 extern "C" int vpb_se_scale(int dtype, const long long* gap_acc, int HW, int C, int sq,
                             const float* w1, const float* b1, const float* w2, const float* b2,
-                            const float* w_proj, int Cout, void* w_scaled, float* scale_out,
-                            void* stream) {
-  return vpb::se_scale_x(dtype, gap_acc, HW, C, sq, w1, b1, w2, b2, w_proj, Cout, w_scaled, nullptr, scale_out,
-                         static_cast<cudaStream_t>(stream));
+                            void* act, float* scale_out, void* stream) {
+  return vpb::se_scale_x(dtype, gap_acc, HW, C, sq, w1, b1, w2, b2, act, nullptr, scale_out, static_cast<cudaStream_t>(stream));
 }
 int vpb::se_scale_x(int dtype, const long long* gap_acc, int HW, int C, int sq, const float* w1, const float* b1,
-                    const float* w2, const float* b2, const float* w_proj, int Cout, void* w_scaled,
-                    void* w_scaled_lo, float* scale_out, cudaStream_t st) {
+                    const float* w2, const float* b2, void* act, void* act_lo, float* scale_out, cudaStream_t st) {
   const size_t smem = (2 * static_cast<size_t>(C) + sq) * sizeof(float);
-  const int grid = std::max(1, std::min(48, (Cout * C / 8 + 1023) / 1024));
+  if ((C & 7) || C > 1152 || sq > 48 || !act) { vpb_set_error("se_scale: unsupported C=%d sq=%d", C, sq); return VPB_ERR_ARG; }
+  // every block recomputes the gate (reads w1 + w2: 8*C*sq bytes), so the grid follows the activation bytes: one block
+  // per 64 KB, at most two waves; the late blocks (C = 1152 on 10x20 pixels) get 7 blocks, the first (96 on 160x320) 148+
+  const int n8 = HW * (C / 8);
+  const int grid = std::max(1, std::min(296, (n8 * 16 + 65535) / 65536));
   if (dtype == VPB_BF16)
     VPB_CUDA_OK(launch_k(se_scale_kernel<BF16>, dim3(grid), dim3(512), smem, st, gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
-                         w_proj, Cout, static_cast<__nv_bfloat16*>(w_scaled), static_cast<__nv_bfloat16*>(w_scaled_lo), scale_out));
+                         static_cast<uint4*>(act), static_cast<uint4*>(act_lo), n8, scale_out));
   else
     VPB_CUDA_OK(launch_k(se_scale_kernel<F16>, dim3(grid), dim3(512), smem, st, gap_acc, 1.0f / HW, C, sq, w1, b1, w2, b2,
-                         w_proj, Cout, static_cast<__half*>(w_scaled), static_cast<__half*>(w_scaled_lo), scale_out));
+                         static_cast<uint4*>(act), static_cast<uint4*>(act_lo), n8, scale_out));
   return VPB_OK;
 }
 

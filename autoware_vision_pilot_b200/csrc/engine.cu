@@ -416,7 +416,7 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
         e.add_op(nm + "dw", "depthwise_kernel", [=](cudaStream_t st) { return depthwise_x(dt, in, in_lo, H, W, ce, k, s_, d_dw, d_dwb, o, o_lo, d_part, st); },
                  2.0 * g.Ho * g.Wo * ce * k * k, 2.0 * H * W * ce + 2.0 * g.Ho * g.Wo * ce);
       }
-      // SE gate folded into the projection weights
+      // SE gate applied to the depthwise output in place (where the reference graph applies it), then a plain 1x1
       const std::string sp = bp + std::to_string(bi + 1) + ".";
       const HostTensor *f1 = find_w_shaped(w, sp + "fc1.weight", {sq, ce, 1, 1}), *b1 = find_w_shaped(w, sp + "fc1.bias", {sq}),
                        *f2 = find_w_shaped(w, sp + "fc2.weight", {ce, sq, 1, 1}), *b2 = find_w_shaped(w, sp + "fc2.bias", {ce});
@@ -427,24 +427,19 @@ static int build_encoder(vp_engine& e, const WeightMap& w, const std::string& p,
         for (int j = 0; j < sq; ++j) f2t[static_cast<size_t>(j) * ce + c] = f2->f[static_cast<size_t>(c) * sq + j];
       float *d_f1 = e.upload_f32(f1->f), *d_b1 = e.upload_f32(b1->f), *d_f2 = e.upload_f32(f2t), *d_b2 = e.upload_f32(b2->f);
       if (!d_part) { vpb_set_error("SE accumulator arena exhausted"); return VPB_ERR_STATE; }
-      std::vector<float> proj(pw->f.size());
-      for (int co = 0; co < cout; ++co)
-        for (int c = 0; c < ce; ++c) proj[static_cast<size_t>(co) * ce + c] = pw->f[static_cast<size_t>(co) * ce + c] * s[co];
-      float* d_proj = e.upload_f32(proj);
+      void* d_wproj = e.upload_16(pack_conv(*pw, &s));            // BatchNorm folded, static
       float* d_pb = e.upload_f32(t);
-      void* d_wscaled = e.dalloc(static_cast<size_t>(cout) * ce * 2 * (e.split ? 2 : 1), false);
-      void* d_wscaled_lo = (e.split && d_wscaled) ? static_cast<uint8_t*>(d_wscaled) + static_cast<size_t>(cout) * ce * 2 : nullptr;
-      if (d_wscaled_lo) e.lo_of[d_wscaled] = d_wscaled_lo;
       {
         const int HW = g.Ho * g.Wo;
+        void* act = dwo.p; void* act_lo = dwo.lo;
         e.add_op(nm + "se", "se_scale_kernel", [=](cudaStream_t st) {
-          return se_scale_x(dt, d_part, HW, ce, sq, d_f1, d_b1, d_f2, d_b2, d_proj, cout, d_wscaled, d_wscaled_lo, nullptr, st);
-        }, 2.0 * (2.0 * ce * sq), 8.0 * ce * kGapReplicas + 8.0 * ce * sq + 4.0 * cout * ce + 2.0 * cout * ce);
+          return se_scale_x(dt, d_part, HW, ce, sq, d_f1, d_b1, d_f2, d_b2, act, act_lo, nullptr, st);
+        }, 2.0 * (2.0 * ce * sq), 8.0 * ce * kGapReplicas + 8.0 * ce * sq + 4.0 * HW * ce);
       }
       // 1x1 project + BN (+ residual; StochasticDepth is identity in eval)
       const bool residual = (s_ == 1 && ci == cout);
       Tens po = e.act_alloc(dwo.H, dwo.W, cout);
-      int rc = e.add_conv(nm + "project", dwo, cout, 1, 1, d_wscaled, d_pb, ACT_NONE,
+      int rc = e.add_conv(nm + "project", dwo, cout, 1, 1, d_wproj, d_pb, ACT_NONE,
                           residual ? VPB_EPI_ADD : VPB_EPI_STORE, &po, residual ? &x : nullptr);
       if (rc) return rc;
       x = po;

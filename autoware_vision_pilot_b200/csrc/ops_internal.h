@@ -51,8 +51,7 @@ int stem_conv_x(int dtype, const void* in, const void* in_lo, int H, int W, cons
 int depthwise_x(int dtype, const void* in, const void* in_lo, int H, int W, int C, int k, int stride, const float* w,
                 const float* bias, void* out, void* out_lo, long long* gap_acc, cudaStream_t st, int act = 1 /* SiLU; 0 = none */);
 int se_scale_x(int dtype, const long long* gap_acc, int HW, int C, int sq, const float* w1, const float* b1,
-               const float* w2, const float* b2, const float* w_proj, int Cout, void* w_scaled, void* w_scaled_lo,
-               float* scale_out, cudaStream_t st);
+               const float* w2, const float* b2, void* act, void* act_lo, float* scale_out, cudaStream_t st);
 int gap_x(int dtype, const void* in, const void* in_lo, int HW, int C, int ld, float* out, cudaStream_t st);
 int ctx_conv1_x(int dtype, const float* in, int H, int W, const float* w, const float* b, int Cout, void* out,
                 void* out_lo, int out_pad, cudaStream_t st, int act = 1 /* ACT_GELU; 2 = ACT_SILU */);

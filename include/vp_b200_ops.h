@@ -157,14 +157,12 @@ int vpb_stem_conv(int dtype, const void* in, int H, int W, const float* w, const
  * in [H][W][C] -> out [Ho][Wo][C]; w fp32 [k*k][C]. */
 int vpb_depthwise(int dtype, const void* in, int H, int W, int C, int k, int stride, const float* w,
                   const float* bias, void* out, long long* gap_acc, void* stream);
-/* squeeze-excitation: mean = gap_acc * 2^-24 / HW; s = sigmoid(W2 silu(W1 mean + b1) + b2); then
- * w_scaled[n][k] = w_proj[n][k] * s[k]  (the channel scale is folded into the following 1x1
- * projection's weights instead of re-writing the activation tensor).
- * w1 fp32 [sq][C], w2 fp32 TRANSPOSED [sq][C], w_proj fp32 [Cout][C] -> w_scaled 16-bit [Cout][C];
- * scale_out (optional) fp32 [C]. */
+/* squeeze-excitation (torchvision SqueezeExcitation): mean = gap_acc * 2^-24 / HW; s = sigmoid(W2 silu(W1 mean + b1) + b2);
+ * then act[p][c] *= s[c] IN PLACE on the depthwise output [HW][C] 16-bit — where the reference graph applies the gate.
+ * (Round 1 folded s into the 16-bit projection weights instead; measured 3-8x less accurate off the calibration frame.)
+ * w1 fp32 [sq][C], w2 fp32 TRANSPOSED [sq][C]; scale_out (optional) fp32 [C]. */
 int vpb_se_scale(int dtype, const long long* gap_acc, int HW, int C, int sq, const float* w1,
-                 const float* b1, const float* w2, const float* b2, const float* w_proj, int Cout,
-                 void* w_scaled, float* scale_out, void* stream);
+                 const float* b1, const float* w2, const float* b2, void* act, float* scale_out, void* stream);
 
 /* ---- context block pieces (scene_context.py:25-57 / auto_steer_context.py:28-60) ---- */
 /* global average pool over [HW][C] 16-bit -> fp32 [C] (scene_context.py:27) */

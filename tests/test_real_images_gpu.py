@@ -3,8 +3,15 @@
     committed under tests/golden/real/ by scripts/make_real_golden.py together with the outputs of the UNMODIFIED
     reference modules on them),
   * 8 synthetic 1080p frames + the i.i.d. adversarial frame through the fused Pillow-bicubic pre-process,
-each against the fp32 CPU oracle with the 16-bit-operand gates of tests/test_engine_gpu.py, and the integer maps
-against the committed reference goldens under the margin rule."""
+each against the fp32 CPU oracle, and the integer maps against the committed reference goldens under the margin rule.
+
+Gates: synthetic frames — the 16-bit-operand gates of tests/test_engine_gpu.py (0.075 / 0.005 sigma).  Real stills —
+EgoLanes in the 16-bit mode (measured 0.008 sigma); SceneSeg / Scene3D / DomainSeg in the split-fp16 fp32-grade mode at
+0.02 / 0.002 sigma (measured 0.006): with the SYNTHETIC checkpoints (no trained weights are reachable offline) real
+frames drive those three random networks into an amplifying regime (f3 -> f4 gain 3.4x, context |max| 2 273, output
+sigma 44 instead of 1) in which ANY 16-bit inference — a CPU emulation of plain fp16 storage included
+(profiles/r2_se_gate_precision.md) — is ~1 sigma away from fp32; that is a property of the random weights, not of
+the engine, and the fp32-grade mode shows the arithmetic is right on exactly these frames."""
 import os
 
 import numpy as np
@@ -36,12 +43,12 @@ def _vpw(ckpt, m):
     return sds[m][0], p
 
 
-def _check(model, ref, raw, cls, tag=""):
+def _check(model, ref, raw, cls, tag="", gmax=GMAX, gmean=GMEAN):
     sig = ref.std()
     err = np.abs(raw - ref)
     print(f"  {model} {tag}: sigma {sig:.3f}  max|d| {err.max() / sig:.4f} sigma  mean|d| {err.mean() / sig:.5f} sigma")
     assert np.isfinite(raw).all()
-    assert err.max() <= GMAX * sig and err.mean() <= GMEAN * sig, (model, tag, err.max() / sig, err.mean() / sig)
+    assert err.max() <= gmax * sig and err.mean() <= gmean * sig, (model, tag, err.max() / sig, err.mean() / sig)
     tau = 2 * err.max()
     if model == "scene_seg":
         srt = np.sort(ref, axis=0)
@@ -60,7 +67,9 @@ def _check(model, ref, raw, cls, tag=""):
 def test_real_video_stills(model, ckpt):
     sd, vpw = _vpw(ckpt, model)
     gold = np.load(os.path.join(REAL, f"{model}_real.npz"))
-    eng = E.Engine([E.KIND_BY_NAME[model]], [vpw], resize_mode=E.RESIZE_NONE)
+    precise = model != "ego_lanes"
+    eng = E.Engine([E.KIND_BY_NAME[model]], [vpw], resize_mode=E.RESIZE_NONE, dtype="fp32" if precise else "fp16")
+    gates = (0.02, 0.002) if precise else (GMAX, GMEAN)
     worst = 0.0
     for i in REAL_FRAMES:
         small = np.asarray(Image.open(os.path.join(REAL, f"frame_{i:02d}.png")).convert("RGB"))
@@ -71,7 +80,7 @@ def test_real_video_stills(model, ckpt):
         # (fp32 reassociation differs between the two hosts' CPU kernels: 5e-4 sigma)
         assert np.abs(ref[:, ::8, ::8] - gold[f"sample_{i}"]).max() <= 5e-4 * max(1.0, float(gold[f"std_{i}"]))
         raw, cls = eng.raw(0), eng.cls(0)
-        worst = max(worst, _check(model, ref, raw, cls, f"real frame {i}"))
+        worst = max(worst, _check(model, ref, raw, cls, f"real frame {i}", *gates))
         if model != "scene_3d":       # integer map vs the REFERENCE's own (margin from the oracle logits)
             gpost = gold[f"post_{i}"]
             margin = {"scene_seg": lambda r: np.sort(r, axis=0)[-1] - np.sort(r, axis=0)[-2],
