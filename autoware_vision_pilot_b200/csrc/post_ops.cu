@@ -319,6 +319,9 @@ extern "C" int vpb_visualize_mask(const uint8_t* mask, int mh, int mw, int viz_t
         tab[VPB_VIZ_EGOLANES][m] = m == 0 ? bgr(255, 0, 0) : (m == 1 ? bgr(255, 0, 200) : (m == 2 ? bgr(0, 153, 0) : 0u));
       }
       VPB_CUDA_OK(cudaMemcpyToSymbol(vpb::g_viz_tab, tab, sizeof(tab)));
+      // pageable upload on the legacy stream: the consuming kernel may run on a non-blocking stream that is not
+      // ordered after it, so drain the device once (one-time, per device)
+      VPB_CUDA_OK(cudaDeviceSynchronize());
       *done = true;
     }
   }

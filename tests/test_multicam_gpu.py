@@ -126,3 +126,38 @@ def test_multicamera_allgather_and_fusion(tmp_path):
         json.dump({"world": world, "payload_bytes": 582624, "allgather_us_max_over_ranks": us,
                    "per_rank_us": [o["allgather_us"] for o in outs]}, f)
     print(f"config5 ok: world {world}, ncclAllGather of 582624 B/rank = {us:.1f} us (max over ranks)")
+
+
+def test_engines_on_two_devices_from_other_threads(tmp_path):
+    """every C-ABI entry point runs under a device guard — engines on two GPUs in ONE process, each driven from
+    a thread whose current device is the OTHER GPU, give the single-engine results."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import threading
+    from autoware_vision_pilot_b200 import engine as E
+    from autoware_vision_pilot_b200 import weights as W
+    from oracle import synth
+    vpw = W.write_vpw(synth.synth_state_dict("ego_lanes"), str(tmp_path / "ego.vpw"))
+    frames = [synth.synth_frame(0), synth.synth_frame(1)]
+    ref = []
+    for f in frames:
+        e = E.Engine([E.EGO_LANES], [vpw], gpu_id=0, resize_mode=E.RESIZE_PIL_BICUBIC)
+        e.infer(f)
+        ref.append(e.raw(0).copy())
+        e.close()
+    engs = [E.Engine([E.EGO_LANES], [vpw], gpu_id=g, resize_mode=E.RESIZE_PIL_BICUBIC) for g in (0, 1)]
+    out = [None, None]
+
+    def work(i):
+        torch.cuda.set_device(1 - i)                      # the "wrong" device is current in this thread
+        for _ in range(3):
+            engs[i].infer(frames[i])
+        out[i] = engs[i].raw(0).copy()
+        assert torch.cuda.current_device() == 1 - i       # the guard restored the caller's device
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert np.array_equal(out[0], ref[0]) and np.array_equal(out[1], ref[1])
