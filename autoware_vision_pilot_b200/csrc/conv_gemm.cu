@@ -89,9 +89,10 @@ struct EpiPix {
 // the scheduler can interleave.  Measured (gpurun_out/bench_conv_v14_nc{1,2}.txt): NC = 2 is 2-3 % SLOWER —
 // 18 warps leave 96 registers per thread (5 warps on two of the SM sub-partitions) and the second chunk
 // spills; only NC = 1 is instantiated.
-template <class E, int NC>
+template <class E, int NC, bool TILEK>
 __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t_row, int n0,
                                                 const float* sbias, int part, const EpiPix& px) {
+  const bool split = TILEK && p.split;       // split-fp16 mode and the post-residual activation exist in the tile kernel only
   const int nchunks = p.BN >> 4;
   typename E::T* out = reinterpret_cast<typename E::T*>(p.out);
   const typename E::T* res = reinterpret_cast<const typename E::T*>(p.res);
@@ -175,7 +176,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
         for (int c = 0; c < NC; ++c)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            rl[c][j] = (p.split && rok[c][j])
+            rl[c][j] = (split && rok[c][j])
                            ? *reinterpret_cast<const uint4*>(res_lo + (px.roff + n0 + (chunk0 + 4 * c) * 16) + 8 * j)
                            : make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -188,12 +189,12 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float2 f = unpack2<E>(rw[i]);
-              if (p.split) { const float2 fl = unpack2<E>(rwl[i]); f.x += fl.x; f.y += fl.y; }
+              if (split) { const float2 fl = unpack2<E>(rwl[i]); f.x += fl.x; f.y += fl.y; }
               float& a = v[c][8 * j + 2 * i];
               float& b = v[c][8 * j + 2 * i + 1];
               if (p.mode == VPB_EPI_ADD) { a += f.x; b += f.y; }
               else { a = fmaf(a, f.x, f.x); b = fmaf(b, f.y, f.y); }
-              if (p.act2 == ACT_SILU) { a = act_silu(a); b = act_silu(b); }
+              if (TILEK && p.act2 == ACT_SILU) { a = act_silu(a); b = act_silu(b); }
             }
           }
       }
@@ -210,7 +211,7 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
             o.z = pack2<E>(v[c][8 * j + 4], v[c][8 * j + 5]);
             o.w = pack2<E>(v[c][8 * j + 6], v[c][8 * j + 7]);
             *reinterpret_cast<uint4*>(op + 8 * j) = o;
-            if (p.split) {          // low half: what the 16-bit rounding of the high half lost
+            if (split) {          // low half: what the 16-bit rounding of the high half lost
               const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
               uint32_t lw[4];
 #pragma unroll
@@ -242,15 +243,20 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
 // cycles per issued instruction, 77 instructions per chunk in the generic form, most of them uniform
 // mode/activation tests and address arithmetic): here pointers advance by constants and nothing is tested
 // inside the loop.
-template <class E, bool GELU>
+// ACT: ACT_NONE | ACT_GELU | ACT_SILU (the encoder's expand / head convolutions); ADD: residual added after the
+// activation (MBConv projection + skip: out = conv + bias + res), the whole N tile inside the residual row as well.
+template <class E, int ACT, bool ADD = false>
 __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32_t t_row, int n0,
                                                     const float* sbias, int part, const EpiPix& px) {
   const int nchunks = p.BN >> 4;
   typename E::T* op = reinterpret_cast<typename E::T*>(p.out) + (px.ooff + n0 + part * 16);
+  const typename E::T* rp = ADD ? reinterpret_cast<const typename E::T*>(p.res) + (px.roff + n0 + part * 16) : nullptr;
   const float4* sb4 = reinterpret_cast<const float4*>(sbias + part * 16);
   uint32_t ta = t_row + part * 16;
   const bool ok = px.ok, zero = px.zero;
-  auto finish = [&](const uint32_t (&rr)[16], const float4* sb, typename E::T* o) {
+  auto finish = [&](const uint32_t (&rr)[16], const float4* sb, typename E::T* o, const typename E::T* r) {
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+    if (ADD && ok) { r0 = reinterpret_cast<const uint4*>(r)[0]; r1 = reinterpret_cast<const uint4*>(r)[1]; }   // in flight early
     float2 v[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -258,9 +264,17 @@ __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32
       v[2 * i] = fadd2(make_float2(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1])), make_float2(b4.x, b4.y));
       v[2 * i + 1] = fadd2(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(b4.z, b4.w));
     }
-    if (GELU) {
+    if (ACT == ACT_GELU) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = act_gelu2(v[i]);
+    } else if (ACT == ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = make_float2(act_silu(v[i].x), act_silu(v[i].y));
+    }
+    if (ADD) {
+      const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fadd2(v[i], unpack2<E>(rw[i]));
     }
     uint4 o0, o1;
     o0.x = pack2<E>(v[0].x, v[0].y); o0.y = pack2<E>(v[1].x, v[1].y); o0.z = pack2<E>(v[2].x, v[2].y); o0.w = pack2<E>(v[3].x, v[3].y);
@@ -279,14 +293,15 @@ __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32
     tmem_ld16(ta, ra);                     // .sync.aligned: every lane takes part, stores are predicated
     tmem_ld16(ta + 64, rb);
     tmem_ld_wait();
-    finish(ra, sb4, op);
-    finish(rb, sb4 + 16, op + 64);
+    finish(ra, sb4, op, rp);
+    finish(rb, sb4 + 16, op + 64, rp + 64);
+    if (ADD) rp += 128;
   }
   if (chunk < nchunks) {
     uint32_t ra[16];
     tmem_ld16(ta, ra);
     tmem_ld_wait();
-    finish(ra, sb4, op);
+    finish(ra, sb4, op, rp);
   }
 }
 
@@ -340,14 +355,19 @@ __device__ __forceinline__ void epilogue_to_smem(const ConvKParams& p, uint32_t 
   }
 }
 
-template <class E>
+// TILEK: the tile kernel (encoder 1x1 convolutions) also gets the lean SiLU and residual-add forms; the 3x3 kernels do
+// not instantiate them (they never use those modes and the extra paths cost them registers / spills).
+template <class E, bool TILEK = false>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, uint32_t t_row, int n0,
                                               const float* sbias, int part, const EpiPix& px) {
   // NC = 2 (two chunks per iteration) measured 2-3 % slower and makes ptxas spill in every kernel that
   // contains it (96-register cap), so only the one-chunk form is instantiated.
-  if (!p.split && p.mode == VPB_EPI_STORE && n0 + p.BN <= p.nlim && p.act == ACT_GELU) epilogue_store_fast<E, true>(p, t_row, n0, sbias, part, px);
-  else if (!p.split && p.mode == VPB_EPI_STORE && n0 + p.BN <= p.nlim && p.act == ACT_NONE) epilogue_store_fast<E, false>(p, t_row, n0, sbias, part, px);
-  else epilogue_chunks<E, 1>(p, t_row, n0, sbias, part, px);
+  const bool whole = !p.split && n0 + p.BN <= p.nlim && p.act2 == ACT_NONE;
+  if (whole && p.mode == VPB_EPI_STORE && p.act == ACT_GELU) epilogue_store_fast<E, ACT_GELU>(p, t_row, n0, sbias, part, px);
+  else if (whole && p.mode == VPB_EPI_STORE && p.act == ACT_NONE) epilogue_store_fast<E, ACT_NONE>(p, t_row, n0, sbias, part, px);
+  else if (TILEK && whole && p.mode == VPB_EPI_STORE && p.act == ACT_SILU) epilogue_store_fast<E, ACT_SILU>(p, t_row, n0, sbias, part, px);
+  else if (TILEK && whole && p.mode == VPB_EPI_ADD && p.act == ACT_NONE && n0 + p.BN <= p.ldr) epilogue_store_fast<E, ACT_NONE, true>(p, t_row, n0, sbias, part, px);
+  else epilogue_chunks<E, 1, TILEK>(p, t_row, n0, sbias, part, px);
 }
 
 __device__ __forceinline__ void stage_bias(const ConvKParams& p, float* dst, int etid, int n0) {
@@ -597,7 +617,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         px.roff = static_cast<uint32_t>((oh + p.res_pad) * (Wo + 2 * p.res_pad) + (ow + p.res_pad)) * p.ldr;
         px.fpix = static_cast<uint32_t>(h * p.W + w);
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride + q4 * 128;
-        epilogue_tile<E>(p, t_row, n0, s_bias[as], part, px);
+        epilogue_tile<E, true>(p, t_row, n0, s_bias[as], part, px);
       }
       tc_fence_before();
       __syncwarp();
@@ -1241,6 +1261,159 @@ conv3x3_splitk_kernel(const __grid_constant__ CUtensorMap mapA,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// (5) weight-stationary ConvTranspose2d(k2, s2) [+ fused 1x1 skip link]
+//
+// The tile kernel re-streams the weights of a (phase, N tile) for every pixel tile: for upsample_layer_3
+// (256 -> 256 at 80x160) that is 128 KB of weights + 48 KB of skip-link operands against 64 KB of activations per tile,
+// 240 KB through the ~61 B/clk L2 -> SM path for 20 MMAs — ncu: tensor pipe 20 %, tile period 12.8 k cycles
+// (profiles/r2_ncu_convt_post.md).  Here a CTA owns ONE weight set (phase, N tile) for the whole launch: all of its K
+// chunks (and the skip link's) are loaded once into shared memory, and only the activation tiles stream through a ring;
+// pixel tiles of a set are dealt round-robin to the CTAs that share it.  Accumulators double-buffered in TMEM, epilogue
+// through swizzled shared-memory slabs and TMA stores (epilogue_to_smem).  Used when a set (<= 96 KB) fits next to the
+// ring and every CTA gets >= 3 pixel tiles (upsample_layer_2 / _3 / _4 of necks and heads).
+// ------------------------------------------------------------------------------------------------
+template <class E>
+__global__ void __launch_bounds__(kThreads, 1)
+convt_ws_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kMaxStages], a_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t b_full;
+  __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_bias[256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_tile_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const int nB = p.kchunks + p.kchunks2;
+  const uint32_t b_base = smem_base + static_cast<uint32_t>(p.stages) * kATileBytes;
+  const uint32_t slab0 = b_base + static_cast<uint32_t>(nB) * b_tile_bytes;
+  // this CTA's weight set and its share of the pixel tiles
+  const int S = p.phases * p.tiles_n;
+  const int set = static_cast<int>(blockIdx.x) % S, j0 = static_cast<int>(blockIdx.x) / S;
+  const int nper = (static_cast<int>(gridDim.x) - set + S - 1) / S;
+  const int ph = static_cast<int>(fast_div(set, p.mg_tn)), nt = set - ph * p.tiles_n, n0 = nt * p.BN;
+  const int npt = p.tiles_h * p.tiles_w;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B); tma_prefetch_desc(&maps.O);
+    if (p.kchunks2) { tma_prefetch_desc(&maps.A2); tma_prefetch_desc(&maps.B2); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
+    mbar_init(smem_u32(&b_full), 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_tfull[s]), 1); mbar_init(smem_u32(&bar_tempty[s]), kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tmem_holder), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {      // the weight set, once (weights are not written by the predecessor, but keep it after pdl_wait: simple)
+      const uint32_t bf = smem_u32(&b_full);
+      mbar_arrive_expect_tx(bf, static_cast<uint32_t>(nB) * b_tile_bytes);
+      for (int c = 0; c < p.kchunks; ++c) tma_load_3d(b_base + c * b_tile_bytes, &maps.B, bf, c * 64, n0, ph);
+      for (int c2 = 0; c2 < p.kchunks2; ++c2) tma_load_3d(b_base + (p.kchunks + c2) * b_tile_bytes, &maps.B2, bf, c2 * 64, n0, 0);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = j0; pt < npt; pt += nper) {
+      const int thi = static_cast<int>(fast_div(pt, p.mg_tw)), twi = pt - thi * p.tiles_w;
+      const int h0 = thi * p.TH, w0 = twi * p.TW;
+      for (int k = 0; k < nB; ++k) {
+        mbar_wait(smem_u32(&a_empty[stage]), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t full = smem_u32(&a_full[stage]);
+          mbar_arrive_expect_tx(full, kATileBytes);
+          if (k < p.kchunks) tma_load_4d(smem_base + stage * kATileBytes, &maps.A, full, k * 64, w0, h0, 0);
+          else tma_load_5d(smem_base + stage * kATileBytes, &maps.A2, full, (k - p.kchunks) * 64, ph & 1, w0, ph >> 1, h0);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc(E::kUmmaFmt, 128, p.BN);
+    mbar_wait(smem_u32(&b_full), 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int pt = j0; pt < npt; pt += nper, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * kAccStride;
+      for (int k = 0; k < nB; ++k) {
+        const int kvalid = k < p.kchunks ? min(64, p.Cin - k * 64) : min(64, p.Cin2 - (k - p.kchunks) * 64);
+        const int ksteps = (kvalid + 15) >> 4;
+        mbar_wait(smem_u32(&a_full[stage]), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = umma_desc_k128(smem_base + stage * kATileBytes);
+          const uint64_t bdesc = umma_desc_k128(b_base + k * b_tile_bytes);
+          for (int kk = 0; kk < ksteps; ++kk) umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&a_empty[stage]));
+          if (k == nB - 1) umma_commit(smem_u32(&bar_tfull[as]));
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (TMEM -> swizzled slabs -> TMA store)
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    const int row = q * 32 + lane;
+    stage_bias(p, s_bias, etid, n0);          // one N tile per CTA: staged once
+    int it = 0;
+    for (int pt = j0; pt < npt; pt += nper, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int thi = static_cast<int>(fast_div(pt, p.mg_tw)), twi = pt - thi * p.tiles_w;
+      mbar_wait(smem_u32(&bar_tfull[as]), aphase);
+      tc_fence_after();
+      if (etid == 0) bulk_wait_read0();       // the previous tile's stores have read the slabs
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      if (p.act == ACT_GELU) epilogue_to_smem<E, true>(p, t_row, s_bias, part, slab0, row);
+      else epilogue_to_smem<E, false>(p, t_row, s_bias, part, slab0, row);
+      fence_proxy_async();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (etid == 0) {
+        for (int sl = 0; sl < (p.BN >> 6); ++sl)
+          tma_store_5d(&maps.O, slab0 + sl * (128 * 128), n0 + sl * 64, ph & 1, twi * p.TW, ph >> 1, thi * p.TH);
+        bulk_commit();
+      }
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+    }
+    if (etid == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1267,6 +1440,8 @@ int device_sm_count() {
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   return n > 0 ? n : 148;
 }
+
+static inline size_t b_bytes_ws(int bn) { return static_cast<size_t>(bn) * 128; }
 
 static int pick_bn(int Cout) {
   if (Cout <= 256) return (Cout + 15) / 16 * 16;
@@ -1492,19 +1667,42 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     // four 128-column accumulators) whenever the N tile is at most 128 wide
     // ... and only when the fused grid still gives >= 2 waves (measured: with fewer tiles the lost
     // parallelism and the single-buffered accumulators cost more than the saved A traffic)
-    p.fuse4 = (a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1 && !a->in2 && !split &&
+    // weight-stationary ConvTranspose kernel: a (phase, N tile) weight set of <= 96 KB resident per CTA
+    p.wstat = 0;
+    if (a->phases == 4 && !split && a->bn <= 0 && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) &&
+        a->dbg_gb != 2 && a->dbg_ms == 0) {
+      const int nB = p.kchunks + p.kchunks2, npt = p.tiles_h * p.tiles_w;
+      for (int bn : {128, 64}) {
+        if (bn > (a->Cout + 63) / 64 * 64) continue;
+        const size_t wbytes = static_cast<size_t>(nB) * bn * 128, slabs = static_cast<size_t>(bn / 64) * 128 * 128;
+        const int tn = (a->Cout + bn - 1) / bn, S = 4 * tn;
+        const long ring = static_cast<long>(kMaxDynSmem) - 1024 - static_cast<long>(wbytes) - static_cast<long>(slabs);
+        if (wbytes > 96 * 1024 || ring < 3 * kATileBytes || S > device_sm_count()) continue;
+        if (static_cast<long>(npt) * S < 3L * device_sm_count()) continue;        // >= 3 pixel tiles per CTA on average
+        p.wstat = 1; p.BN = bn; p.tiles_n = tn;
+        p.stages = static_cast<int>(std::min<long>(kMaxStages, ring / kATileBytes));
+        break;
+      }
+    }
+    p.fuse4 = (!p.wstat && a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1 && !a->in2 && !split &&
                (p.tiles_h * p.tiles_w * p.tiles_n >= 2 * device_sm_count() || a->dbg_ms == 2)) ? 1 : 0;
     p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * (p.fuse4 ? 1 : p.phases);
     const size_t stage_bytes = kATileBytes + b_bytes * (p.fuse4 ? 4 : 1);
     // staged TMA-store epilogue: plain store (ConvTranspose, with or without the fused skip link) or GELU, N tile made
     // of whole 64-channel slabs; dbg_gb == 2 forces the direct-store epilogue (A/B comparison)
-    p.tma_store = (!split && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) && p.BN % 64 == 0 &&
-                   a->phases == 4 && a->dbg_gb != 2) ? 1 : 0;
+    p.tma_store = (p.wstat || (!split && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) && p.BN % 64 == 0 &&
+                               a->phases == 4 && a->dbg_gb != 2)) ? 1 : 0;
     const size_t slab_bytes = p.tma_store ? static_cast<size_t>(p.BN / 64) * 128 * 128 : 0;
     int stages = static_cast<int>((kMaxDynSmem - 1024 - slab_bytes) / stage_bytes);
-    if (stages < 2 && p.tma_store) { p.tma_store = 0; stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes); }
-    p.stages = std::max(2, std::min(stages, kMaxStages));
-    plan->smem_bytes = p.stages * stage_bytes + (p.tma_store ? slab_bytes : 0) + 1024;
+    if (stages < 2 && p.tma_store && !p.wstat) { p.tma_store = 0; stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes); }
+    if (p.wstat) {
+      plan->smem_bytes = static_cast<size_t>(p.stages) * kATileBytes + static_cast<size_t>(p.kchunks + p.kchunks2) * b_bytes_ws(p.BN) +
+                         static_cast<size_t>(p.BN / 64) * 128 * 128 + 1024;
+      p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * 4;
+    } else {
+      p.stages = std::max(2, std::min(stages, kMaxStages));
+      plan->smem_bytes = p.stages * stage_bytes + (p.tma_store ? slab_bytes : 0) + 1024;
+    }
   }
   p.mg_tn = fast_div_magic(p.tiles_n); p.mg_tw = fast_div_magic(lin ? 1 : p.tiles_w);
   p.mg_tpp = fast_div_magic(lin ? 1 : p.tiles_n * p.tiles_h * p.tiles_w); p.mg_wp = fast_div_magic(p.WP);
@@ -1513,7 +1711,8 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.out_f32 = a->out_f32; p.out_cls = a->out_cls;
   p.trace = a->dbg_trace;
   plan->dtype = a->dtype;
-  plan->grid = p.splitk ? p.total_tiles * p.splitk
+  plan->grid = p.wstat ? std::min(p.total_tiles, device_sm_count())
+             : p.splitk ? p.total_tiles * p.splitk
              : p.pair ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
                       : std::min(p.total_tiles, device_sm_count());
   plan->flops = 2.0 * a->H * a->W * static_cast<double>(a->Cout) * a->phases * (a->Cin * a->taps + p.Cin2);
@@ -1654,6 +1853,8 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
       VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_splitk_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_splitk_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(convt_ws_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(convt_ws_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       *done = true;
     }
   }
@@ -1672,7 +1873,10 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     ConvMaps maps;
     maps.A = plan->mapA; maps.B = plan->mapB; maps.A2 = plan->mapA2; maps.B2 = plan->mapB2; maps.O = plan->mapO;
     maps.Alo = plan->mapAlo; maps.Blo = plan->mapBlo; maps.A2lo = plan->mapA2lo; maps.B2lo = plan->mapB2lo;
-    if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, maps, plan->p));
+    if (plan->p.wstat) {
+      if (bf) VPB_CUDA_OK(launch_k(convt_ws_kernel<BF16>, g, b, plan->smem_bytes, stream, maps, plan->p));
+      else VPB_CUDA_OK(launch_k(convt_ws_kernel<F16>, g, b, plan->smem_bytes, stream, maps, plan->p));
+    } else if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, maps, plan->p));
     else VPB_CUDA_OK(launch_k(conv_gemm_kernel<F16>, g, b, plan->smem_bytes, stream, maps, plan->p));
   }
   return VPB_OK;

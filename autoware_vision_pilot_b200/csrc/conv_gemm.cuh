@@ -20,6 +20,8 @@ struct ConvKParams {
   int stages;                    // smem pipeline depth (tile kernel)
   int lin;                       // 1 = linear-padded 3x3 kernel
   int fuse4;                     // tile kernel, ConvTranspose: all 4 phases per CTA tile
+  int wstat;                     // weight-stationary ConvTranspose kernel (convt_ws_kernel): a CTA keeps ONE (phase, N tile)
+                                 // weight set resident in shared memory and streams pixel tiles through it
   int tma_store;                 // tile kernel: epilogue stages the tile in shared memory and writes it with TMA stores
   int nlim;                      // channels of an output row that may be written: ldo, or round8(Cout) for a channel SLICE
   int stride;                    // tile kernel: 1 | 2 (input sampled through the tensor map's traversal stride)

@@ -277,7 +277,7 @@ struct vp_engine {
     plans.push_back(std::move(plan));
     OpRec op; op.name = name; op.flops = pp->flops; op.gemm = true; op.lane = cur_lane;
     op.kind = pp->p.lin ? (pp->p.pair ? 3 : 2) : 1;
-    op.kname = !pp->p.lin ? "conv_gemm_kernel" : pp->p.splitk ? "conv3x3_splitk_kernel" : pp->p.pair ? "conv3x3_pair_kernel" : "conv3x3_lin_kernel";
+    op.kname = pp->p.wstat ? "convt_ws_kernel" : !pp->p.lin ? "conv_gemm_kernel" : pp->p.splitk ? "conv3x3_splitk_kernel" : pp->p.pair ? "conv3x3_pair_kernel" : "conv3x3_lin_kernel";
     op.launch = [pp](cudaStream_t s) { return conv_plan_launch(pp, s); };
     ops.push_back(std::move(op));
     return VPB_OK;

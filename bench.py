@@ -68,7 +68,7 @@ def load_traffic():
 
 
 TENSOR_KERNELS = ("conv_gemm_kernel", "conv3x3_lin_kernel", "conv3x3_pair_kernel", "conv3x3_splitk_kernel",
-                  "conv3x3_dx_kernel", "convt_fused_kernel")
+                  "convt_ws_kernel")
 
 
 def stage_rooflines(eng, peaks):
