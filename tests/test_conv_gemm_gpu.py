@@ -129,7 +129,9 @@ def test_conv_transpose_phases(H, W, Cin, Cout):
     (10, 20, 128, 128, 112, 0, 1),     # neck block 0 shape class: skip = f3 (112 ch, K tail 64+48)
     (20, 40, 96, 72, 40, 0, 0),        # K tails on both inputs, N tail
     (40, 80, 64, 256, 24, 1, 1),       # zero-bordered skip tensor
-    (80, 160, 256, 256, 16, 0, 1),     # up3 of the SceneSeg head at full size (skip = f0, 16 ch)
+    (80, 160, 256, 256, 16, 0, 1),     # up3 of the SceneSeg head at full size (skip = f0, 16 ch): weight-stationary kernel
+    (40, 80, 512, 512, 24, 0, 1),      # upsample_layer_2 of the neck (skip = f1): weight-stationary kernel, N tile 64
+    (80, 160, 256, 200, 32, 1, 1),     # weight-stationary kernel with an N tail and a zero-bordered skip tensor
 ])
 def test_conv_transpose_with_fused_skip_link(H, W, Cin, Cout, C2, pad2, out_pad):
     """out = ConvTranspose2d(in) + Conv1x1(skip) in one kernel (scene_neck.py:30-32): the skip link is a
@@ -206,3 +208,23 @@ def test_conv_full_size_decode8():
     ref = F.gelu(_ref_conv(x, w, b, 9, 128)).permute(1, 2, 0)
     err = (out.float() - ref).abs()
     assert (err <= 1.5e-3 + 1e-3 * ref.abs()).all(), err.max().item()
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout,act", [(160, 320, 128, 128, L.ACT_NONE), (96, 200, 64, 64, L.ACT_GELU)])
+def test_conv_transpose_weight_stationary_no_skip(H, W, Cin, Cout, act):
+    """upsample_layer_4 (scene_seg_head.py:16) at full size: the weight-stationary kernel without a skip input, into a
+    zero-bordered output; ragged pixel tiles (96 x 200) with the GELU epilogue."""
+    _setup()
+    from tests.gpu_util import conv_gemm
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(H, W, Cin, generator=g).half().cuda()
+    wt = (torch.randn(Cin, Cout, 2, 2, generator=g) / Cin ** 0.5).half().cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    w_pnc = wt.permute(2, 3, 1, 0).reshape(4, Cout, Cin).contiguous()
+    _, _, out = conv_gemm(x, w_pnc, b, taps=1, phases=4, act=act, out_pad=1)
+    assert (out[0] == 0).all() and (out[-1] == 0).all() and (out[:, 0] == 0).all() and (out[:, -1] == 0).all()
+    ref = F.conv_transpose2d(x.float().permute(2, 0, 1).unsqueeze(0), wt.float(), b, stride=2)[0].permute(1, 2, 0)
+    if act == L.ACT_GELU:
+        ref = F.gelu(ref)
+    err = (out[1:-1, 1:-1, :Cout].float() - ref).abs()
+    assert (err <= 2e-3 + 1e-3 * ref.abs()).all(), err.max().item()
