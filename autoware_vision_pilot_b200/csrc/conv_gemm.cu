@@ -1672,7 +1672,10 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     if (a->phases == 4 && !split && a->bn <= 0 && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) &&
         a->dbg_gb != 2 && a->dbg_ms == 0) {
       const int nB = p.kchunks + p.kchunks2, npt = p.tiles_h * p.tiles_w;
-      for (int bn : {128, 64}) {
+      // N tile 128 only: measured (gpurun_out/r2j_bench_conv.txt) upsample_layer_4 23.1 -> 18.0 us, upsample_layer_3 17.3 ->
+      // 16.1 us, but upsample_layer_2 with the 64-wide tiles its 144 KB weight sets would need: 16.7 -> 25.2 us (A re-read
+      // 32x, half-rate N = 64 MMAs, 4-vs-5 CTAs per set imbalance) -> layers whose 128-wide set does not fit keep the tile kernel
+      for (int bn : {128}) {
         if (bn > (a->Cout + 63) / 64 * 64) continue;
         const size_t wbytes = static_cast<size_t>(nB) * bn * 128, slabs = static_cast<size_t>(bn / 64) * 128 * 128;
         const int tn = (a->Cout + bn - 1) / bn, S = 4 * tn;
