@@ -1263,19 +1263,21 @@ conv3x3_splitk_kernel(const __grid_constant__ CUtensorMap mapA,
 
 
 // ------------------------------------------------------------------------------------------------
-// (5) weight-stationary ConvTranspose2d(k2, s2) [+ fused 1x1 skip link]
+// (5) weight-stationary ConvTranspose2d(k2, s2) [+ fused 1x1 skip link] on a CTA pair
 //
 // The tile kernel re-streams the weights of a (phase, N tile) for every pixel tile: for upsample_layer_3
-// (256 -> 256 at 80x160) that is 128 KB of weights + 48 KB of skip-link operands against 64 KB of activations per tile,
-// 240 KB through the ~61 B/clk L2 -> SM path for 20 MMAs — ncu: tensor pipe 20 %, tile period 12.8 k cycles
-// (profiles/r2_ncu_convt_post.md).  Here a CTA owns ONE weight set (phase, N tile) for the whole launch: all of its K
-// chunks (and the skip link's) are loaded once into shared memory, and only the activation tiles stream through a ring;
-// pixel tiles of a set are dealt round-robin to the CTAs that share it.  Accumulators double-buffered in TMEM, epilogue
-// through swizzled shared-memory slabs and TMA stores (epilogue_to_smem).  Used when a set (<= 96 KB) fits next to the
-// ring and every CTA gets >= 3 pixel tiles (upsample_layer_2 / _3 / _4 of necks and heads).
+// (256 -> 256 at 80x160) that is 128 KB of weights + 48 KB of skip-link operands against 64 KB of activations per tile —
+// ncu: tensor pipe 20 %, tile period 12.8 k cycles (profiles/r2_ncu_convt_post.md).  Here a CTA PAIR (cluster of 2,
+// tcgen05.mma.cta_group::2, M = 256 = two pixel tiles) owns ONE weight set (phase, N tile) for the whole launch: every K
+// chunk of it (and of the skip link) is loaded once, HALF of its rows into each CTA, and only the activation tiles stream
+// through a ring; pixel-tile pairs of a set are dealt round-robin to the clusters that share it.  The in-kernel timeline
+// of the single-CTA form of this kernel (gpurun_out/r2k_trace_ws_up3.txt) showed it MMA-issue bound at ~140 cycles per
+// M128 x N128 MMA (8 KB of operands per 64 cycles of math against the ~64 B/clk shared-memory operand path); the pair
+// halves the weight bytes per CTA, so N = 256 (4 + 4 KB per 128 cycles) runs at the full rate.  Accumulators
+// double-buffered in TMEM, epilogue per CTA through swizzled shared-memory slabs and TMA stores (epilogue_to_smem).
 // ------------------------------------------------------------------------------------------------
 template <class E>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 convt_ws_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxStages], a_empty[kMaxStages];
@@ -1286,17 +1288,19 @@ convt_ws_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_tile_bytes = static_cast<uint32_t>(p.BN) * 128u;
+  const uint32_t bh_bytes = static_cast<uint32_t>(p.BN >> 1) * 128u;      // this CTA's half of a weight chunk
   const int nB = p.kchunks + p.kchunks2;
   const uint32_t b_base = smem_base + static_cast<uint32_t>(p.stages) * kATileBytes;
-  const uint32_t slab0 = b_base + static_cast<uint32_t>(nB) * b_tile_bytes;
-  // this CTA's weight set and its share of the pixel tiles
+  const uint32_t slab0 = b_base + static_cast<uint32_t>(nB) * bh_bytes;
+  // this cluster's weight set and its share of the pixel-tile pairs
   const int S = p.phases * p.tiles_n;
-  const int set = static_cast<int>(blockIdx.x) % S, j0 = static_cast<int>(blockIdx.x) / S;
-  const int nper = (static_cast<int>(gridDim.x) - set + S - 1) / S;
+  const int set = cid % S, j0 = cid / S;
+  const int nper = (ncl - set + S - 1) / S;
   const int ph = static_cast<int>(fast_div(set, p.mg_tn)), nt = set - ph * p.tiles_n, n0 = nt * p.BN;
-  const int npt = p.tiles_h * p.tiles_w;
+  const int npt = p.tiles_h * p.tiles_w, npairs = (npt + 1) >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B); tma_prefetch_desc(&maps.O);
@@ -1305,112 +1309,129 @@ convt_ws_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
     mbar_init(smem_u32(&b_full), 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_tfull[s]), 1); mbar_init(smem_u32(&bar_tempty[s]), kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_tfull[s]), 1); mbar_init(smem_u32(&bar_tempty[s]), 2 * kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(&tmem_holder), 512);
-    tmem_relinquish();
+    tmem_alloc2(smem_u32(&tmem_holder), 512);
+    tmem_relinquish2();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();          // peer barriers initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
   pdl_launch_dependents();
   pdl_wait();
+  const bool tr = p.trace && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) p.trace[255] = clock64();
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (elect_one()) {      // the weight set, once (weights are not written by the predecessor, but keep it after pdl_wait: simple)
-      const uint32_t bf = smem_u32(&b_full);
-      mbar_arrive_expect_tx(bf, static_cast<uint32_t>(nB) * b_tile_bytes);
-      for (int c = 0; c < p.kchunks; ++c) tma_load_3d(b_base + c * b_tile_bytes, &maps.B, bf, c * 64, n0, ph);
-      for (int c2 = 0; c2 < p.kchunks2; ++c2) tma_load_3d(b_base + (p.kchunks + c2) * b_tile_bytes, &maps.B2, bf, c2 * 64, n0, 0);
+    // ------------------------------------------------------------ TMA producer (both CTAs: own pixels, own half of B)
+    if (elect_one()) {
+      const uint32_t bf = smem_u32(&b_full) & kPeerBitMask;
+      if (rank == 0) mbar_arrive_expect_tx(bf, 2u * static_cast<uint32_t>(nB) * bh_bytes);
+      const int nr = n0 + static_cast<int>(rank) * (p.BN >> 1);
+      for (int c = 0; c < p.kchunks; ++c) tma_load_3d_pair(b_base + c * bh_bytes, &maps.B, bf, c * 64, nr, ph);
+      for (int c2 = 0; c2 < p.kchunks2; ++c2) tma_load_3d_pair(b_base + (p.kchunks + c2) * bh_bytes, &maps.B2, bf, c2 * 64, nr, 0);
     }
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    for (int pt = j0; pt < npt; pt += nper) {
+    for (int pp = j0; pp < npairs; pp += nper) {
+      const int pt = 2 * pp + static_cast<int>(rank);       // may be == npt for an odd count: every row out of bounds -> zeros
       const int thi = static_cast<int>(fast_div(pt, p.mg_tw)), twi = pt - thi * p.tiles_w;
       const int h0 = thi * p.TH, w0 = twi * p.TW;
       for (int k = 0; k < nB; ++k) {
         mbar_wait(smem_u32(&a_empty[stage]), phase ^ 1u);
         if (elect_one()) {
-          const uint32_t full = smem_u32(&a_full[stage]);
-          mbar_arrive_expect_tx(full, kATileBytes);
-          if (k < p.kchunks) tma_load_4d(smem_base + stage * kATileBytes, &maps.A, full, k * 64, w0, h0, 0);
-          else tma_load_5d(smem_base + stage * kATileBytes, &maps.A2, full, (k - p.kchunks) * 64, ph & 1, w0, ph >> 1, h0);
+          const uint32_t full = smem_u32(&a_full[stage]) & kPeerBitMask;
+          if (rank == 0) mbar_arrive_expect_tx(full, 2u * kATileBytes);
+          if (k < p.kchunks) tma_load_4d_pair(smem_base + stage * kATileBytes, &maps.A, full, k * 64, w0, h0, 0);
+          else tma_load_5d_pair(smem_base + stage * kATileBytes, &maps.A2, full, (k - p.kchunks) * 64, ph & 1, w0, ph >> 1, h0);
+          if (tr) { const int ti = (pp - j0) / nper; if (ti < 8 && (k == 0 || k == nB - 1)) p.trace[ti * 16 + (k ? 1 : 0)] = clock64(); }
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc(E::kUmmaFmt, 128, p.BN);
-    mbar_wait(smem_u32(&b_full), 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int pt = j0; pt < npt; pt += nper, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * kAccStride;
-      for (int k = 0; k < nB; ++k) {
-        const int kvalid = k < p.kchunks ? min(64, p.Cin - k * 64) : min(64, p.Cin2 - (k - p.kchunks) * 64);
-        const int ksteps = (kvalid + 15) >> 4;
-        mbar_wait(smem_u32(&a_full[stage]), phase);
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc(E::kUmmaFmt, 256, p.BN);
+      mbar_wait(smem_u32(&b_full), 0);
+      if (tr && lane == 0) p.trace[254] = clock64();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pp = j0; pp < npairs; pp += nper, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t adesc = umma_desc_k128(smem_base + stage * kATileBytes);
-          const uint64_t bdesc = umma_desc_k128(b_base + k * b_tile_bytes);
-          for (int kk = 0; kk < ksteps; ++kk) umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-          umma_commit(smem_u32(&a_empty[stage]));
-          if (k == nB - 1) umma_commit(smem_u32(&bar_tfull[as]));
+        if (tr && lane == 0 && it < 8) p.trace[it * 16 + 9] = clock64();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int k = 0; k < nB; ++k) {
+          const int kvalid = k < p.kchunks ? min(64, p.Cin - k * 64) : min(64, p.Cin2 - (k - p.kchunks) * 64);
+          const int ksteps = (kvalid + 15) >> 4;
+          mbar_wait(smem_u32(&a_full[stage]), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = umma_desc_k128(smem_base + stage * kATileBytes);
+            const uint64_t bdesc = umma_desc_k128(b_base + k * bh_bytes);
+            if (tr && it < 8 && k == 0) p.trace[it * 16 + 4] = clock64();
+            for (int kk = 0; kk < ksteps; ++kk) umma_f16_2cta(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            umma_commit_pair(smem_u32(&a_empty[stage]));
+            if (k == nB - 1) { umma_commit_pair(smem_u32(&bar_tfull[as])); if (tr && it < 8) p.trace[it * 16 + 8] = clock64(); }
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (TMEM -> swizzled slabs -> TMA store)
+    // ------------------------------------------------------------ epilogue (both CTAs: own 128 pixels x BN channels)
     const int q = warp & 3;
     const int part = (warp - 2) >> 2;
     const int etid = threadIdx.x - 64;
     const int row = q * 32 + lane;
-    stage_bias(p, s_bias, etid, n0);          // one N tile per CTA: staged once
+    stage_bias(p, s_bias, etid, n0);          // one N tile per cluster: staged once
     int it = 0;
-    for (int pt = j0; pt < npt; pt += nper, ++it) {
+    for (int pp = j0; pp < npairs; pp += nper, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int pt = 2 * pp + static_cast<int>(rank);
       const int thi = static_cast<int>(fast_div(pt, p.mg_tw)), twi = pt - thi * p.tiles_w;
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
+      if (tr && etid == 0 && it < 8) p.trace[it * 16 + 10] = clock64();
       if (etid == 0) bulk_wait_read0();       // the previous tile's stores have read the slabs
       asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (tr && etid == 0 && it < 8) p.trace[it * 16 + 11] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
       if (p.act == ACT_GELU) epilogue_to_smem<E, true>(p, t_row, s_bias, part, slab0, row);
       else epilogue_to_smem<E, false>(p, t_row, s_bias, part, slab0, row);
       fence_proxy_async();
       tc_fence_before();
       asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (etid == 0) {
+      if (tr && etid == 0 && it < 8) p.trace[it * 16 + 12] = clock64();
+      if (etid == 0 && pt < npt) {
         for (int sl = 0; sl < (p.BN >> 6); ++sl)
           tma_store_5d(&maps.O, slab0 + sl * (128 * 128), n0 + sl * 64, ph & 1, twi * p.TW, ph >> 1, thi * p.TH);
         bulk_commit();
+        if (tr && it < 8) p.trace[it * 16 + 13] = clock64();
       }
-      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&bar_tempty[as]), 0);
     }
-    if (etid == 0) bulk_wait0();
+    if (etid == 0) { bulk_wait0(); if (tr) p.trace[253] = clock64(); }
   }
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();          // the leader's MMAs read the peer's shared memory until the very end
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -1671,17 +1692,16 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     p.wstat = 0;
     if (a->phases == 4 && !split && a->bn <= 0 && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) &&
         a->dbg_gb != 2 && a->dbg_ms == 0) {
-      const int nB = p.kchunks + p.kchunks2, npt = p.tiles_h * p.tiles_w;
-      // N tile 128 only: measured (gpurun_out/r2j_bench_conv.txt) upsample_layer_4 23.1 -> 18.0 us, upsample_layer_3 17.3 ->
-      // 16.1 us, but upsample_layer_2 with the 64-wide tiles its 144 KB weight sets would need: 16.7 -> 25.2 us (A re-read
-      // 32x, half-rate N = 64 MMAs, 4-vs-5 CTAs per set imbalance) -> layers whose 128-wide set does not fit keep the tile kernel
-      for (int bn : {128}) {
-        if (bn > (a->Cout + 63) / 64 * 64) continue;
-        const size_t wbytes = static_cast<size_t>(nB) * bn * 128, slabs = static_cast<size_t>(bn / 64) * 128 * 128;
+      // CTA pair: each CTA holds HALF of the set's rows; widest N tile whose half set fits next to the slabs and a ring of
+      // >= 3 activation tiles, with at least one pixel-tile pair per cluster
+      const int nB = p.kchunks + p.kchunks2, npairs = (p.tiles_h * p.tiles_w + 1) / 2, ncl = std::max(1, device_sm_count() / 2);
+      for (int bn : {256, 128}) {
+        if (bn > (a->Cout + 127) / 128 * 128 || a->dbg_pair < 0) continue;
+        const size_t wbytes = static_cast<size_t>(nB) * (bn / 2) * 128, slabs = static_cast<size_t>(bn / 64) * 128 * 128;
         const int tn = (a->Cout + bn - 1) / bn, S = 4 * tn;
         const long ring = static_cast<long>(kMaxDynSmem) - 1024 - static_cast<long>(wbytes) - static_cast<long>(slabs);
-        if (wbytes > 96 * 1024 || ring < 3 * kATileBytes || S > device_sm_count()) continue;
-        if (static_cast<long>(npt) * S < 3L * device_sm_count()) continue;        // >= 3 pixel tiles per CTA on average
+        if (ring < 3 * kATileBytes || S > ncl) continue;
+        if (static_cast<long>(npairs) * S < ncl) continue;
         p.wstat = 1; p.BN = bn; p.tiles_n = tn;
         p.stages = static_cast<int>(std::min<long>(kMaxStages, ring / kATileBytes));
         break;
@@ -1699,9 +1719,9 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     int stages = static_cast<int>((kMaxDynSmem - 1024 - slab_bytes) / stage_bytes);
     if (stages < 2 && p.tma_store && !p.wstat) { p.tma_store = 0; stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes); }
     if (p.wstat) {
-      plan->smem_bytes = static_cast<size_t>(p.stages) * kATileBytes + static_cast<size_t>(p.kchunks + p.kchunks2) * b_bytes_ws(p.BN) +
+      plan->smem_bytes = static_cast<size_t>(p.stages) * kATileBytes + static_cast<size_t>(p.kchunks + p.kchunks2) * b_bytes_ws(p.BN / 2) +
                          static_cast<size_t>(p.BN / 64) * 128 * 128 + 1024;
-      p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * 4;
+      p.total_tiles = ((p.tiles_h * p.tiles_w + 1) / 2) * p.tiles_n * 4;      // pixel-tile pairs x weight sets
     } else {
       p.stages = std::max(2, std::min(stages, kMaxStages));
       plan->smem_bytes = p.stages * stage_bytes + (p.tma_store ? slab_bytes : 0) + 1024;
@@ -1714,7 +1734,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.out_f32 = a->out_f32; p.out_cls = a->out_cls;
   p.trace = a->dbg_trace;
   plan->dtype = a->dtype;
-  plan->grid = p.wstat ? std::min(p.total_tiles, device_sm_count())
+  plan->grid = p.wstat ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
              : p.splitk ? p.total_tiles * p.splitk
              : p.pair ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
                       : std::min(p.total_tiles, device_sm_count());
@@ -1761,7 +1781,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
       cuuint64_t dims[3] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->Cout),
                             static_cast<cuuint64_t>(a->taps * a->phases)};
       cuuint64_t strides[2] = {static_cast<cuuint64_t>(ldw) * 2, static_cast<cuuint64_t>(ldw) * 2 * a->Cout};
-      cuuint32_t box[3] = {64, static_cast<cuuint32_t>(p.pair ? p.BN / 2 : p.BN), 1};
+      cuuint32_t box[3] = {64, static_cast<cuuint32_t>((p.pair || p.wstat) ? p.BN / 2 : p.BN), 1};
       cuuint32_t es[3] = {1, 1, 1};
       return enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, es,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1827,7 +1847,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     auto encB2 = [&](const void* ptr, CUtensorMap* m) {
       cuuint64_t bd[3] = {static_cast<cuuint64_t>(a->Cin2), static_cast<cuuint64_t>(a->Cout), 1};
       cuuint64_t bs[2] = {static_cast<cuuint64_t>(a->Cin2) * 2, static_cast<cuuint64_t>(a->Cin2) * 2 * a->Cout};
-      cuuint32_t bb[3] = {64, static_cast<cuuint32_t>(p.BN), 1};
+      cuuint32_t bb[3] = {64, static_cast<cuuint32_t>(p.wstat ? p.BN / 2 : p.BN), 1};
       cuuint32_t be[3] = {1, 1, 1};
       return enc(m, dt, 3, const_cast<void*>(ptr), bd, bs, bb, be,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
