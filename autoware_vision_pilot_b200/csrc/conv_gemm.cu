@@ -311,10 +311,13 @@ __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32
 // path's one-request-per-cycle limit, and it is what bounds the ConvTranspose layers (they write 4x the pixels they
 // read).  Here every 16-column chunk goes to shared memory in the 128-byte-swizzled box layout ([128 pixels][64 ch]
 // per slab: 4 wavefronts per warp store, the minimum) and one thread then issues a TMA store per 64-channel slab.
+// chunk0 / nck >= 0: this warp drains the nck CONSECUTIVE chunks starting at chunk0 (slab-group form used by
+// convt_ws_kernel, where the four quadrant warps of a slab run their own barrier and store); nck < 0: the interleaved
+// assignment chunk = part, part + 4, ... of the tile kernel.
 template <class E, bool GELU>
 __device__ __forceinline__ void epilogue_to_smem(const ConvKParams& p, uint32_t t_row, const float* sbias, int part,
-                                                 uint32_t slab0, int row) {
-  const int nchunks = p.BN >> 4;
+                                                 uint32_t slab0, int row, int chunk0 = 0, int nck = -1) {
+  const int nchunks = nck >= 0 ? chunk0 + nck : (p.BN >> 4);
   const uint32_t rbase = slab0 + static_cast<uint32_t>(row) * 128u;
   const uint32_t rx = static_cast<uint32_t>(row & 7);
   auto finish = [&](const uint32_t (&rr)[16], int chunk) {
@@ -338,14 +341,15 @@ __device__ __forceinline__ void epilogue_to_smem(const ConvKParams& p, uint32_t 
     st_shared_v4(slab + ((j ^ rx) << 4), o0);
     st_shared_v4(slab + (((j + 1u) ^ rx) << 4), o1);
   };
-  int chunk = part;
-  for (; chunk + 4 < nchunks; chunk += 8) {
+  const int step = nck >= 0 ? 1 : 4;
+  int chunk = nck >= 0 ? chunk0 : part;
+  for (; chunk + step < nchunks; chunk += 2 * step) {
     uint32_t ra[16], rb[16];
     tmem_ld16(t_row + chunk * 16, ra);
-    tmem_ld16(t_row + (chunk + 4) * 16, rb);
+    tmem_ld16(t_row + (chunk + step) * 16, rb);
     tmem_ld_wait();
     finish(ra, chunk);
-    finish(rb, chunk + 4);
+    finish(rb, chunk + step);
   }
   if (chunk < nchunks) {
     uint32_t ra[16];
@@ -1396,6 +1400,11 @@ convt_ws_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
     const int etid = threadIdx.x - 64;
     const int row = q * 32 + lane;
     stage_bias(p, s_bias, etid, n0);          // one N tile per cluster: staged once
+    // slab groups: nslab = BN / 64 in {1, 2, 4}; part p drains chunks [p * nslab, (p + 1) * nslab) = slab p * nslab / 4
+    const int nslab = p.BN >> 6;
+    const int slab = (part * nslab) >> 2;
+    const int gthreads = 512 / nslab;
+    const bool gleader = (q == 0) && (lane == 0) && (part == (slab * 4) / nslab);
     int it = 0;
     for (int pp = j0; pp < npairs; pp += nper, ++it) {
       const int as = it & 1;
@@ -1404,26 +1413,28 @@ convt_ws_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       const int thi = static_cast<int>(fast_div(pt, p.mg_tw)), twi = pt - thi * p.tiles_w;
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
-      if (tr && etid == 0 && it < 8) p.trace[it * 16 + 10] = clock64();
-      if (etid == 0) bulk_wait_read0();       // the previous tile's stores have read the slabs
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (tr && etid == 0 && it < 8) p.trace[it * 16 + 11] = clock64();
+      if (tr && gleader && slab == 0 && it < 8) p.trace[it * 16 + 10] = clock64();
+      // every 64-channel slab has its own group of warps, its own barrier and its own store: a slab's store is in
+      // flight while the other slabs are still being drained, and only that slab's previous store is waited for
+      // (the single-buffer form cost ~1.5 k cycles of waiting per tile, gpurun_out/r2l_trace_ws_up3.txt)
+      if (gleader) bulk_wait_read0();
+      named_bar_sync(2 + slab, gthreads);
+      if (tr && gleader && slab == 0 && it < 8) p.trace[it * 16 + 11] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
-      if (p.act == ACT_GELU) epilogue_to_smem<E, true>(p, t_row, s_bias, part, slab0, row);
-      else epilogue_to_smem<E, false>(p, t_row, s_bias, part, slab0, row);
+      if (p.act == ACT_GELU) epilogue_to_smem<E, true>(p, t_row, s_bias, part, slab0, row, part * nslab, nslab);
+      else epilogue_to_smem<E, false>(p, t_row, s_bias, part, slab0, row, part * nslab, nslab);
       fence_proxy_async();
       tc_fence_before();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (tr && etid == 0 && it < 8) p.trace[it * 16 + 12] = clock64();
-      if (etid == 0 && pt < npt) {
-        for (int sl = 0; sl < (p.BN >> 6); ++sl)
-          tma_store_5d(&maps.O, slab0 + sl * (128 * 128), n0 + sl * 64, ph & 1, twi * p.TW, ph >> 1, thi * p.TH);
+      named_bar_sync(2 + slab, gthreads);
+      if (tr && gleader && slab == 0 && it < 8) p.trace[it * 16 + 12] = clock64();
+      if (gleader && pt < npt) {
+        tma_store_5d(&maps.O, slab0 + slab * (128 * 128), n0 + slab * 64, ph & 1, twi * p.TW, ph >> 1, thi * p.TH);
         bulk_commit();
-        if (tr && it < 8) p.trace[it * 16 + 13] = clock64();
+        if (tr && slab == 0 && it < 8) p.trace[it * 16 + 13] = clock64();
       }
       if (lane == 0) mbar_arrive_cluster(smem_u32(&bar_tempty[as]), 0);
     }
-    if (etid == 0) { bulk_wait0(); if (tr) p.trace[253] = clock64(); }
+    if (gleader) { bulk_wait0(); if (tr && slab == 0) p.trace[253] = clock64(); }
   }
 
   tc_fence_before();
