@@ -1713,6 +1713,10 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
         const long ring = static_cast<long>(kMaxDynSmem) - 1024 - static_cast<long>(wbytes) - static_cast<long>(slabs);
         if (ring < 3 * kATileBytes || S > ncl) continue;
         if (static_cast<long>(npairs) * S < ncl) continue;
+        // measured per layer (gpurun_out/r2l_bench_conv.txt, tile kernel -> this kernel): upsample_layer_1 16.9 -> 14.6 us,
+        // _3 17.3 -> 12.9, _4 23.1 -> 18.3, but _2 (512 -> 512 at 40x80: 9 K chunks against a 7-slot ring, 3 rounds of
+        // 36-MMA tiles) 16.7 -> 18.3: long K loops with many pixel-tile pairs stay on the tile kernel
+        if (nB >= 8 && npairs >= 8) continue;
         p.wstat = 1; p.BN = bn; p.tiles_n = tn;
         p.stages = static_cast<int>(std::min<long>(kMaxStages, ring / kATileBytes));
         break;
