@@ -314,9 +314,12 @@ __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32
 // chunk0 / nck >= 0: this warp drains the nck CONSECUTIVE chunks starting at chunk0 (slab-group form used by
 // convt_ws_kernel, where the four quadrant warps of a slab run their own barrier and store); nck < 0: the interleaved
 // assignment chunk = part, part + 4, ... of the tile kernel.
-template <class E, bool GELU>
+// CLS / gb: the upconv kernel's border pixels take their bias row from global memory (gb != nullptr: this lane's pixel is on
+// the image border, where the folded ConvTranspose bias sees fewer 3x3 taps) instead of the staged interior row.
+template <class E, bool GELU, bool CLS = false>
 __device__ __forceinline__ void epilogue_to_smem(const ConvKParams& p, uint32_t t_row, const float* sbias, int part,
-                                                 uint32_t slab0, int row, int chunk0 = 0, int nck = -1) {
+                                                 uint32_t slab0, int row, int chunk0 = 0, int nck = -1,
+                                                 const float* gb = nullptr) {
   const int nchunks = nck >= 0 ? chunk0 + nck : (p.BN >> 4);
   const uint32_t rbase = slab0 + static_cast<uint32_t>(row) * 128u;
   const uint32_t rx = static_cast<uint32_t>(row & 7);
@@ -325,7 +328,9 @@ __device__ __forceinline__ void epilogue_to_smem(const ConvKParams& p, uint32_t 
     float2 v[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b4 = sb[i];
+      float4 b4;
+      if (CLS && gb) b4 = __ldg(reinterpret_cast<const float4*>(gb + chunk * 16) + i);
+      else b4 = sb[i];
       v[2 * i] = fadd2(make_float2(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1])), make_float2(b4.x, b4.y));
       v[2 * i + 1] = fadd2(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(b4.z, b4.w));
     }
@@ -1446,6 +1451,218 @@ convt_ws_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// (6) "upconv": ConvTranspose2d(k2, s2) [+ Conv1x1(skip)] followed by Conv3x3 + bias + GELU, as ONE GEMM on a CTA pair
+//
+// The reference sums the ConvTranspose and the skip link without an activation and feeds the sum to a 3x3 convolution
+// (scene_neck.py:30-37, scene_seg_head.py:25-33), so the two linear layers compose exactly: output phase (a, b) — the
+// pixels (2h+a, 2w+b) — is a 2x2 convolution of the LOW-resolution input with weights
+//     Wf[a,b][ty,tx] = sum over the 3x3 taps (dy,dx) that land on low-res offset (ty-1+a, tx-1+b) of  W3[dy,dx] . Wt[a',b']
+// plus a 3x3 convolution of the skip tensor with W3[dy,dx] . Wskip, plus a bias that depends only on which 3x3 taps fall
+// inside the image (9 border classes).  K per output pixel drops from 9*Cmid (+ Cin + C2 for the ConvTranspose) to
+// 4*Cin + 9*C2, the upsampled tensor is never written or read, and one kernel replaces two (vpb_upconv_compose builds the
+// weights at load time; DESIGN.md 3e has the algebra and the flop table).
+// Tile = (phase, N tile, pair of 128-pixel low-res tiles); stage = this CTA's 128 x 64 activation box + HALF of the
+// BN x 64 weight box (tcgen05.mma.cta_group::2, M = 256); accumulators double-buffered in TMEM; epilogue per 64-channel
+// slab through swizzled shared memory and a TMA store into the [h][a][w][b][c] view of the output (as convt_ws_kernel).
+// ------------------------------------------------------------------------------------------------
+template <class E>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+upconv_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bh_bytes = static_cast<uint32_t>(p.BN >> 1) * 128u;      // this CTA's half of a weight box
+  const uint32_t stage_bytes = kATileBytes + bh_bytes;
+  const int nslab = p.BN >> 6;
+  const uint32_t slab0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (slab0 - smem_u32(smem_raw)) + nslab * (128 * 128));   // [tiles_n * BN]
+  const int npt = p.tiles_h * p.tiles_w, npairs = (npt + 1) >> 1;
+  const int kc1 = p.kchunks, kc2 = p.kchunks2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.A); tma_prefetch_desc(&maps.B); tma_prefetch_desc(&maps.O);
+    if (kc2) { tma_prefetch_desc(&maps.A2); tma_prefetch_desc(&maps.B2); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_tfull[s]), 1); mbar_init(smem_u32(&bar_tempty[s]), 2 * kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(smem_u32(&tmem_holder), 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // peer barriers initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();
+  const bool tr = p.trace && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) p.trace[255] = clock64();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs: own pixels, own half of the weights)
+    int stage = 0;
+    uint32_t phase = 0;
+    int ti = 0;
+    for (int tile = cid; tile < p.total_tiles; tile += ncl, ++ti) {
+      const int set = static_cast<int>(fast_div(tile, p.mg_tpp)), pp = tile - set * npairs;
+      const int ph = static_cast<int>(fast_div(set, p.mg_tn)), nt = set - ph * p.tiles_n;
+      const int pt = 2 * pp + static_cast<int>(rank);       // may be == npt for an odd count: every row out of bounds -> zeros
+      const int thi = static_cast<int>(fast_div(pt, p.mg_tw)), twi = pt - thi * p.tiles_w;
+      const int h0 = thi * p.TH, w0 = twi * p.TW, pa = ph >> 1, pb = ph & 1;
+      const int nr = nt * p.BN + static_cast<int>(rank) * (p.BN >> 1);
+      // the four low-resolution taps of this phase: offsets (ty - 1 + a, tx - 1 + b)
+      for (int t = 0; t < 4; ++t) {
+        const int oy = (t >> 1) - 1 + pa, ox = (t & 1) - 1 + pb;
+        for (int c = 0; c < kc1; ++c) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          if (elect_one()) {
+            const uint32_t full = smem_u32(&bar_full[stage]) & kPeerBitMask;
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            if (rank == 0) mbar_arrive_expect_tx(full, 2u * stage_bytes);
+            tma_load_4d_pair(sa, &maps.A, full, c * 64, w0 + ox, h0 + oy, 0);
+            tma_load_3d_pair(sa + kATileBytes, &maps.B, full, c * 64, nr, ph * 4 + t);
+            if (tr && ti < 8) { if (t == 0 && c == 0) p.trace[ti * 16] = clock64(); if (t == 3 && c == kc1 - 1) p.trace[ti * 16 + 1] = clock64(); }
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+      // the nine taps of the skip tensor (output resolution, [h][a][w][b][c] view): hi-res row 2h + a + dy - 1 is low-res
+      // row h + floor(u / 2) of row phase u & 1, u = a + dy - 1; rows / columns outside the image are zero-filled by TMA
+      if (kc2) {
+        for (int t2 = 0; t2 < 9; ++t2) {
+          const int dy = t2 / 3, dx = t2 - dy * 3;
+          const int u = pa + dy - 1, v = pb + dx - 1;
+          for (int c2 = 0; c2 < kc2; ++c2) {
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            if (elect_one()) {
+              const uint32_t full = smem_u32(&bar_full[stage]) & kPeerBitMask;
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              if (rank == 0) mbar_arrive_expect_tx(full, 2u * stage_bytes);
+              tma_load_5d_pair(sa, &maps.A2, full, c2 * 64, v & 1, w0 + (v >> 1), u & 1, h0 + (u >> 1));
+              tma_load_3d_pair(sa + kATileBytes, &maps.B2, full, c2 * 64, nr, t2);
+              if (tr && ti < 8 && t2 == 8 && c2 == kc2 - 1) p.trace[ti * 16 + 2] = clock64();
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc(E::kUmmaFmt, 256, p.BN);
+      const int n1 = 4 * kc1, nK = n1 + 9 * kc2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cid; tile < p.total_tiles; tile += ncl, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1u);
+        tc_fence_after();
+        if (tr && lane == 0 && it < 8) p.trace[it * 16 + 9] = clock64();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        int c = 0;                    // K chunk inside the current tap
+        for (int k = 0; k < nK; ++k) {
+          if (k == n1) c = 0;
+          const int kvalid = k < n1 ? min(64, p.Cin - c * 64) : min(64, p.Cin2 - c * 64);
+          if (++c == (k < n1 ? kc1 : kc2)) c = 0;
+          const int ksteps = (kvalid + 15) >> 4;
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint64_t adesc = umma_desc_k128(sa);
+            const uint64_t bdesc = umma_desc_k128(sa + kATileBytes);
+            if (tr && it < 8) { if (k == 0) p.trace[it * 16 + 4] = clock64(); if (k == nK - 1) p.trace[it * 16 + 8] = clock64(); }
+            if (ksteps == 4) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_f16_2cta(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            } else {
+              for (int kk = 0; kk < ksteps; ++kk) umma_f16_2cta(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair(smem_u32(&bar_empty[stage]));
+            if (k == nK - 1) umma_commit_pair(smem_u32(&bar_tfull[as]));
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (both CTAs: own 128 pixels x BN channels)
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    const int row = q * 32 + lane;
+    const int lh = row >> p.tw_shift, lw = row & (p.TW - 1);
+    // interior bias row (class 4) of every N tile, staged once
+    for (int n = etid; n < p.tiles_n * p.BN; n += 512) s_bias[n] = n < p.Cout ? __ldg(p.bias + 4 * p.Cout + n) : 0.f;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    const int slab = (part * nslab) >> 2;
+    const int gthreads = 512 / nslab;
+    const bool gleader = (q == 0) && (lane == 0) && (part == (slab * 4) / nslab);
+    int it = 0;
+    for (int tile = cid; tile < p.total_tiles; tile += ncl, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int set = static_cast<int>(fast_div(tile, p.mg_tpp)), pp = tile - set * npairs;
+      const int ph = static_cast<int>(fast_div(set, p.mg_tn)), nt = set - ph * p.tiles_n, n0 = nt * p.BN;
+      const int pt = 2 * pp + static_cast<int>(rank);
+      const int thi = static_cast<int>(fast_div(pt, p.mg_tw)), twi = pt - thi * p.tiles_w;
+      const int pa = ph >> 1, pb = ph & 1;
+      const int h = thi * p.TH + lh, w = twi * p.TW + lw;
+      // border class of this lane's output pixel (2h + a, 2w + b): first / interior / last row and column
+      const int cy = (pa == 0 && h == 0) ? 0 : (pa == 1 && h == p.H - 1) ? 2 : 1;
+      const int cx = (pb == 0 && w == 0) ? 0 : (pb == 1 && w == p.W - 1) ? 2 : 1;
+      const int cls = cy * 3 + cx;
+      const float* gb = cls != 4 ? p.bias + cls * p.Cout + n0 : nullptr;
+      mbar_wait(smem_u32(&bar_tfull[as]), aphase);
+      tc_fence_after();
+      if (tr && gleader && slab == 0 && it < 8) p.trace[it * 16 + 10] = clock64();
+      if (gleader) bulk_wait_read0();          // this slab's previous store has read the shared memory
+      named_bar_sync(2 + slab, gthreads);
+      if (tr && gleader && slab == 0 && it < 8) p.trace[it * 16 + 11] = clock64();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      if (p.act == ACT_GELU) epilogue_to_smem<E, true, true>(p, t_row, s_bias + n0, part, slab0, row, part * nslab, nslab, gb);
+      else epilogue_to_smem<E, false, true>(p, t_row, s_bias + n0, part, slab0, row, part * nslab, nslab, gb);
+      fence_proxy_async();
+      tc_fence_before();
+      named_bar_sync(2 + slab, gthreads);
+      if (tr && gleader && slab == 0 && it < 8) p.trace[it * 16 + 12] = clock64();
+      if (gleader && pt < npt) {
+        tma_store_5d(&maps.O, slab0 + slab * (128 * 128), n0 + slab * 64, pb, twi * p.TW, pa, thi * p.TH);
+        bulk_commit();
+      }
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&bar_tempty[as]), 0);
+    }
+    if (gleader) { bulk_wait0(); if (tr && slab == 0) p.trace[253] = clock64(); }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the leader's MMAs read the peer's shared memory until the very end
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1502,7 +1719,13 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     return VPB_ERR_ARG;
   }
   if (a->act2 != ACT_NONE && a->act2 != ACT_SILU) { vpb_set_error("conv: act2 supports SiLU only"); return VPB_ERR_ARG; }
-  if (!((a->taps == 9 && a->phases == 1) || (a->taps == 1 && (a->phases == 1 || a->phases == 4)))) {
+  const bool upc = a->taps == 4 && a->phases == 4;       // fused ConvTranspose -> Conv3x3 (upconv_pair_kernel)
+  if (upc && (a->algo == VPB_ALGO_LINEAR || a->in_lo || a->mode != VPB_EPI_STORE || (a->act != ACT_NONE && a->act != ACT_GELU) ||
+              !a->bias || (a->Cout & 15) || a->out_slice || cstride != 1 || a->ldw || (a->in2 && a->taps2 != 9))) {
+    vpb_set_error("conv: upconv (taps=4, phases=4) needs the TILE algorithm, 16-bit mode, STORE, act NONE|GELU, bias[9][Cout], Cout%%16==0, taps2=9 with in2");
+    return VPB_ERR_ARG;
+  }
+  if (!((a->taps == 9 && a->phases == 1) || (a->taps == 1 && (a->phases == 1 || a->phases == 4)) || upc)) {
     vpb_set_error("conv: unsupported taps=%d phases=%d", a->taps, a->phases);
     return VPB_ERR_ARG;
   }
@@ -1535,7 +1758,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     }
   }
   if (a->in2) {
-    if (lin || a->taps != 1 || !a->w2 || a->Cin2 <= 0 || (a->Cin2 & 7) || (a->ld2 & 7) || a->ld2 < a->Cin2) {
+    if (lin || (a->taps != 1 && !upc) || !a->w2 || a->Cin2 <= 0 || (a->Cin2 & 7) || (a->ld2 & 7) || a->ld2 < a->Cin2) {
       vpb_set_error("conv: second input needs the TILE algorithm, taps=1, w2, Cin2/ld2 multiples of 8 (Cin2=%d ld2=%d)",
                     a->Cin2, a->ld2);
       return VPB_ERR_ARG;
@@ -1567,7 +1790,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
   p.desc_bo = a->dbg_base_offset ? 1 : 0;
   p.WP = a->W + 2; p.NP = (a->H + 2) * (a->W + 2);
   p.BN = a->bn > 0 ? a->bn : pick_bn(a->Cout);
-  if (a->bn <= 0 && a->phases == 4 && a->Cout > 64 && p.BN % 64) {
+  if (a->bn <= 0 && a->phases == 4 && !upc && a->Cout > 64 && p.BN % 64) {
     // ConvTranspose: N tiles made of whole 64-channel slabs (the TMA-store epilogue writes one box per slab)
     int best = 256, best_waste = 1 << 30;
     for (int bn = 256; bn >= 128; bn -= 64) {
@@ -1599,7 +1822,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     if (S >= 2) { p.splitk = S; p.BN = bn; }
   }
   bool convt_fused_bn = false;
-  if (a->bn <= 0 && a->phases == 4 && p.BN > 128) {
+  if (a->bn <= 0 && a->phases == 4 && !upc && p.BN > 128) {
     // ConvTranspose: the fused form (all four phases per tile, 4 accumulators) needs an N tile <= 128;
     // it only pays with >= 2 waves of fused tiles, otherwise keep the wide tile (measured: up3 at
     // BN=256 20 us, at BN=128 unfused 26 us)
@@ -1617,7 +1840,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     if (a->dbg_ms == 2 || (a->dbg_ms != 1 && !a->in2 && sp * ((a->Cout + best - 1) / best) >= 2 * device_sm_count()))
       { p.BN = best; convt_fused_bn = true; }
   }
-  if (!convt_fused_bn && !p.splitk && a->bn <= 0 && a->Cout >= 128) {
+  if (!convt_fused_bn && !p.splitk && !upc && a->bn <= 0 && a->Cout >= 128) {
     // small-M layers (context, first neck blocks): trade N-tile width for CTA count so that the
     // persistent grid covers more of the 148 SMs (weights are re-streamed from L2, activations
     // are tiny)
@@ -1701,7 +1924,23 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     // parallelism and the single-buffered accumulators cost more than the saved A traffic)
     // weight-stationary ConvTranspose kernel: a (phase, N tile) weight set of <= 96 KB resident per CTA
     p.wstat = 0;
-    if (a->phases == 4 && !split && a->bn <= 0 && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) &&
+    p.upc = upc ? 1 : 0; p.taps2 = a->in2 ? a->taps2 : 0;
+    if (upc) {
+      // N tile: fewest (waves x cycles per K chunk) on the 74 clusters; an M256 x N MMA of one K chunk costs ~512 / 384 /
+      // 256 cycles at N = 256 / 128 / 64 (narrow tiles are bound by the shared-memory operand path, conv_gemm.cu header)
+      const int npairs = (p.tiles_h * p.tiles_w + 1) / 2, ncl = std::max(1, device_sm_count() / 2);
+      int best = 0; long best_t = -1;
+      for (int bn : {256, 128, 64}) {
+        if (a->bn > 0 ? bn != a->bn : bn > (a->Cout + 63) / 64 * 64) continue;
+        const int tn = (a->Cout + bn - 1) / bn;
+        const long waves = (static_cast<long>(npairs) * 4 * tn + ncl - 1) / ncl;
+        const long t = waves * (bn == 256 ? 512 : bn == 128 ? 384 : 256);
+        if (best_t < 0 || t < best_t) { best_t = t; best = bn; }
+      }
+      if (!best) { vpb_set_error("conv: upconv N tile must be 64, 128 or 256 (bn=%d)", a->bn); return VPB_ERR_ARG; }
+      p.BN = best; p.tiles_n = (a->Cout + best - 1) / best;
+    }
+    if (a->phases == 4 && !upc && !split && a->bn <= 0 && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) &&
         a->dbg_gb != 2 && a->dbg_ms == 0) {
       // CTA pair: each CTA holds HALF of the set's rows; widest N tile whose half set fits next to the slabs and a ring of
       // >= 3 activation tiles, with at least one pixel-tile pair per cluster
@@ -1722,18 +1961,25 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
         break;
       }
     }
-    p.fuse4 = (!p.wstat && a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1 && !a->in2 && !split &&
+    p.fuse4 = (!p.wstat && !p.upc && a->phases == 4 && p.BN <= 128 && a->dbg_ms != 1 && !a->in2 && !split &&
                (p.tiles_h * p.tiles_w * p.tiles_n >= 2 * device_sm_count() || a->dbg_ms == 2)) ? 1 : 0;
     p.total_tiles = p.tiles_h * p.tiles_w * p.tiles_n * (p.fuse4 ? 1 : p.phases);
     const size_t stage_bytes = kATileBytes + b_bytes * (p.fuse4 ? 4 : 1);
     // staged TMA-store epilogue: plain store (ConvTranspose, with or without the fused skip link) or GELU, N tile made
     // of whole 64-channel slabs; dbg_gb == 2 forces the direct-store epilogue (A/B comparison)
-    p.tma_store = (p.wstat || (!split && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) && p.BN % 64 == 0 &&
+    p.tma_store = (p.wstat || p.upc || (!split && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) && p.BN % 64 == 0 &&
                                a->phases == 4 && a->dbg_gb != 2)) ? 1 : 0;
     const size_t slab_bytes = p.tma_store ? static_cast<size_t>(p.BN / 64) * 128 * 128 : 0;
     int stages = static_cast<int>((kMaxDynSmem - 1024 - slab_bytes) / stage_bytes);
-    if (stages < 2 && p.tma_store && !p.wstat) { p.tma_store = 0; stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes); }
-    if (p.wstat) {
+    if (stages < 2 && p.tma_store && !p.wstat && !p.upc) { p.tma_store = 0; stages = static_cast<int>((kMaxDynSmem - 1024) / stage_bytes); }
+    if (p.upc) {
+      const size_t st = kATileBytes + static_cast<size_t>(p.BN / 2) * 128, bias_b = (static_cast<size_t>(p.tiles_n) * p.BN * 4 + 1023) / 1024 * 1024;
+      const long ring = static_cast<long>(kMaxDynSmem) - 1024 - static_cast<long>(slab_bytes) - static_cast<long>(bias_b);
+      p.stages = static_cast<int>(std::min<long>(kMaxStages, ring / static_cast<long>(st)));
+      if (p.stages < 3) { vpb_set_error("conv: upconv ring does not fit"); return VPB_ERR_ARG; }
+      plan->smem_bytes = p.stages * st + slab_bytes + bias_b + 1024;
+      p.total_tiles = ((p.tiles_h * p.tiles_w + 1) / 2) * p.tiles_n * 4;      // pixel-tile pairs x (phase, N tile)
+    } else if (p.wstat) {
       plan->smem_bytes = static_cast<size_t>(p.stages) * kATileBytes + static_cast<size_t>(p.kchunks + p.kchunks2) * b_bytes_ws(p.BN / 2) +
                          static_cast<size_t>(p.BN / 64) * 128 * 128 + 1024;
       p.total_tiles = ((p.tiles_h * p.tiles_w + 1) / 2) * p.tiles_n * 4;      // pixel-tile pairs x weight sets
@@ -1743,17 +1989,17 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     }
   }
   p.mg_tn = fast_div_magic(p.tiles_n); p.mg_tw = fast_div_magic(lin ? 1 : p.tiles_w);
-  p.mg_tpp = fast_div_magic(lin ? 1 : p.tiles_n * p.tiles_h * p.tiles_w); p.mg_wp = fast_div_magic(p.WP);
+  p.mg_tpp = fast_div_magic(lin ? 1 : p.upc ? (p.tiles_h * p.tiles_w + 1) / 2 : p.tiles_n * p.tiles_h * p.tiles_w); p.mg_wp = fast_div_magic(p.WP);
   p.act = a->act; p.mode = a->mode; p.final_kind = a->final_kind;
   p.bias = a->bias; p.out = a->out; p.ldo = a->ldo; p.res = a->res; p.ldr = a->ldr;
   p.out_f32 = a->out_f32; p.out_cls = a->out_cls;
   p.trace = a->dbg_trace;
   plan->dtype = a->dtype;
-  plan->grid = p.wstat ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
+  plan->grid = (p.wstat || p.upc) ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
              : p.splitk ? p.total_tiles * p.splitk
              : p.pair ? 2 * std::min(p.total_tiles, device_sm_count() / 2)
                       : std::min(p.total_tiles, device_sm_count());
-  plan->flops = 2.0 * a->H * a->W * static_cast<double>(a->Cout) * a->phases * (a->Cin * a->taps + p.Cin2);
+  plan->flops = 2.0 * a->H * a->W * static_cast<double>(a->Cout) * a->phases * (a->Cin * a->taps + p.Cin2 * (upc ? 9 : 1));
 
   const CUtensorMapDataType dt =
       a->dtype == VPB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -1796,7 +2042,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
       cuuint64_t dims[3] = {static_cast<cuuint64_t>(a->Cin), static_cast<cuuint64_t>(a->Cout),
                             static_cast<cuuint64_t>(a->taps * a->phases)};
       cuuint64_t strides[2] = {static_cast<cuuint64_t>(ldw) * 2, static_cast<cuuint64_t>(ldw) * 2 * a->Cout};
-      cuuint32_t box[3] = {64, static_cast<cuuint32_t>((p.pair || p.wstat) ? p.BN / 2 : p.BN), 1};
+      cuuint32_t box[3] = {64, static_cast<cuuint32_t>((p.pair || p.wstat || p.upc) ? p.BN / 2 : p.BN), 1};
       cuuint32_t es[3] = {1, 1, 1};
       return enc(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, es,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1860,9 +2106,9 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
       return VPB_ERR_CUDA;
     }
     auto encB2 = [&](const void* ptr, CUtensorMap* m) {
-      cuuint64_t bd[3] = {static_cast<cuuint64_t>(a->Cin2), static_cast<cuuint64_t>(a->Cout), 1};
+      cuuint64_t bd[3] = {static_cast<cuuint64_t>(a->Cin2), static_cast<cuuint64_t>(a->Cout), static_cast<cuuint64_t>(p.upc ? 9 : 1)};
       cuuint64_t bs[2] = {static_cast<cuuint64_t>(a->Cin2) * 2, static_cast<cuuint64_t>(a->Cin2) * 2 * a->Cout};
-      cuuint32_t bb[3] = {64, static_cast<cuuint32_t>(p.wstat ? p.BN / 2 : p.BN), 1};
+      cuuint32_t bb[3] = {64, static_cast<cuuint32_t>((p.wstat || p.upc) ? p.BN / 2 : p.BN), 1};
       cuuint32_t be[3] = {1, 1, 1};
       return enc(m, dt, 3, const_cast<void*>(ptr), bd, bs, bb, be,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1893,6 +2139,8 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
       VPB_CUDA_OK(cudaFuncSetAttribute(conv3x3_splitk_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       VPB_CUDA_OK(cudaFuncSetAttribute(convt_ws_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       VPB_CUDA_OK(cudaFuncSetAttribute(convt_ws_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(upconv_pair_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      VPB_CUDA_OK(cudaFuncSetAttribute(upconv_pair_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
       *done = true;
     }
   }
@@ -1911,7 +2159,10 @@ int conv_plan_launch(const ConvPlan* plan, cudaStream_t stream) {
     ConvMaps maps;
     maps.A = plan->mapA; maps.B = plan->mapB; maps.A2 = plan->mapA2; maps.B2 = plan->mapB2; maps.O = plan->mapO;
     maps.Alo = plan->mapAlo; maps.Blo = plan->mapBlo; maps.A2lo = plan->mapA2lo; maps.B2lo = plan->mapB2lo;
-    if (plan->p.wstat) {
+    if (plan->p.upc) {
+      if (bf) VPB_CUDA_OK(launch_k(upconv_pair_kernel<BF16>, g, b, plan->smem_bytes, stream, maps, plan->p));
+      else VPB_CUDA_OK(launch_k(upconv_pair_kernel<F16>, g, b, plan->smem_bytes, stream, maps, plan->p));
+    } else if (plan->p.wstat) {
       if (bf) VPB_CUDA_OK(launch_k(convt_ws_kernel<BF16>, g, b, plan->smem_bytes, stream, maps, plan->p));
       else VPB_CUDA_OK(launch_k(convt_ws_kernel<F16>, g, b, plan->smem_bytes, stream, maps, plan->p));
     } else if (bf) VPB_CUDA_OK(launch_k(conv_gemm_kernel<BF16>, g, b, plan->smem_bytes, stream, maps, plan->p));

@@ -22,6 +22,9 @@ struct ConvKParams {
   int fuse4;                     // tile kernel, ConvTranspose: all 4 phases per CTA tile
   int wstat;                     // weight-stationary ConvTranspose kernel (convt_ws_kernel): a CTA keeps ONE (phase, N tile)
                                  // weight set resident in shared memory and streams pixel tiles through it
+  int upc;                       // upconv_pair_kernel: fused ConvTranspose2d(k2,s2) [+ 1x1 skip] -> Conv3x3 (taps = 4 low-res taps per output
+                                 // phase, taps2 = 9 skip taps, bias = [9 border classes][Cout])
+  int taps2;
   int tma_store;                 // tile kernel: epilogue stages the tile in shared memory and writes it with TMA stores
   int nlim;                      // channels of an output row that may be written: ldo, or round8(Cout) for a channel SLICE
   int stride;                    // tile kernel: 1 | 2 (input sampled through the tensor map's traversal stride)

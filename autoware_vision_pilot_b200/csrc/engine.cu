@@ -98,7 +98,8 @@ struct Tens {  // NHWC 16-bit activation, channel stride == C; pad = 1: zero-bor
 struct OpRec {
   std::string name;
   std::function<int(cudaStream_t)> launch;
-  double flops = 0;
+  double flops = 0;     // 2*MAC this launch executes
+  double flops_ref = -1; // 2*MAC of the reference's layers this op stands for (< 0: same as flops)
   double bytes = 0;     // algorithmic HBM bytes per launch (HBM-bound stages; SURVEY.md 8d definitions)
   std::string kname;    // kernel the op launches (roofline report groups launches by kernel)
   bool gemm = false;
@@ -251,7 +252,7 @@ struct vp_engine {
   int add_conv(const std::string& name, const Tens& in, int Cout, int taps, int phases, const void* w,
                const float* bias, int act, int mode, const Tens* out, const Tens* res,
                int final_kind = 0, float* out_f32 = nullptr, uint8_t* out_cls = nullptr,
-               const Tens* in2 = nullptr, const void* w2 = nullptr) {
+               const Tens* in2 = nullptr, const void* w2 = nullptr, int taps2 = 0) {
     vpb_conv_args a{};
     a.dtype = dtype; a.H = in.H; a.W = in.W; a.Cin = in.C; a.ldi = in.C;
     a.Cout = Cout; a.taps = taps; a.phases = phases; a.act = act; a.mode = mode;
@@ -269,7 +270,7 @@ struct vp_engine {
       if (in2) { a.in2_lo = in2->lo; a.w2_lo = lo(w2); }
     }
     a.out_f32 = out_f32; a.out_cls = out_cls;
-    if (in2) { a.in2 = in2->p; a.w2 = w2; a.Cin2 = in2->C; a.ld2 = in2->C; a.in2_pad = in2->pad; }
+    if (in2) { a.in2 = in2->p; a.w2 = w2; a.Cin2 = in2->C; a.ld2 = in2->C; a.in2_pad = in2->pad; a.taps2 = taps2; }
     auto plan = std::make_unique<ConvPlan>();
     int rc = conv_plan_build(&a, plan.get());
     if (rc != VPB_OK) return rc;
@@ -277,7 +278,7 @@ struct vp_engine {
     plans.push_back(std::move(plan));
     OpRec op; op.name = name; op.flops = pp->flops; op.gemm = true; op.lane = cur_lane;
     op.kind = pp->p.lin ? (pp->p.pair ? 3 : 2) : 1;
-    op.kname = pp->p.wstat ? "convt_ws_kernel" : !pp->p.lin ? "conv_gemm_kernel" : pp->p.splitk ? "conv3x3_splitk_kernel" : pp->p.pair ? "conv3x3_pair_kernel" : "conv3x3_lin_kernel";
+    op.kname = pp->p.upc ? "upconv_pair_kernel" : pp->p.wstat ? "convt_ws_kernel" : !pp->p.lin ? "conv_gemm_kernel" : pp->p.splitk ? "conv3x3_splitk_kernel" : pp->p.pair ? "conv3x3_pair_kernel" : "conv3x3_lin_kernel";
     op.launch = [pp](cudaStream_t s) { return conv_plan_launch(pp, s); };
     ops.push_back(std::move(op));
     return VPB_OK;
@@ -501,6 +502,79 @@ static int up_skip(vp_engine& e, const WeightMap& w, const std::string& p, int i
                     VPB_EPI_STORE, out, nullptr, 0, nullptr, nullptr, skip, dw2);
 }
 
+// ConvTranspose2d(k2,s2) [+ Conv1x1(skip)] and the Conv3x3 + GELU that follows it (scene_neck.py:30-37,
+// scene_seg_head.py:25-33) as ONE GEMM over the low-resolution tensor: no activation separates the layers, so their
+// weights are composed once at load time (vpb_upconv_compose, upconv_compose.cu) and the upsampled tensor is never
+// materialised.  16-bit mode only — the split-fp16 mode keeps the reference's layer-by-layer graph.  VPB_UPCONV=0
+// switches the fusion off (A/B measurements).
+static bool upconv_enabled(const vp_engine& e) {
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("VPB_UPCONV"); v = (s && s[0] == '0') ? 0 : 1; }
+  return v != 0 && !e.split;
+}
+static int upconv_layer(vp_engine& e, const WeightMap& w, const std::string& p, int i, int dec, const std::string& tag,
+                        const Tens& in, const Tens* skip, Tens* out) {
+  const std::string uk = p + "upsample_layer_" + std::to_string(i), dk = p + "decode_layer_" + std::to_string(dec);
+  const HostTensor* ut = find_w_shaped(w, uk + ".weight", {in.C, -1, 2, 2});
+  const HostTensor* ub = ut ? find_w_shaped(w, uk + ".bias", {ut->dims[1]}) : nullptr;
+  if (!ut || !ub) return VPB_ERR_IO;
+  const int Cin = in.C, Cmid = ut->dims[1];
+  const HostTensor* w3 = find_w_shaped(w, dk + ".weight", {-1, Cmid, 3, 3});
+  const HostTensor* b3 = w3 ? find_w_shaped(w, dk + ".bias", {w3->dims[0]}) : nullptr;
+  if (!w3 || !b3) return VPB_ERR_IO;
+  const int Cout = w3->dims[0];
+  const HostTensor *st = nullptr, *sb = nullptr;
+  int C2 = 0;
+  if (skip) {
+    const std::string sk = p + "skip_link_layer_" + std::to_string(i);
+    st = find_w_shaped(w, sk + ".weight", {Cmid, skip->C, 1, 1}); sb = find_w_shaped(w, sk + ".bias", {Cmid});
+    if (!st || !sb) return VPB_ERR_IO;
+    if (skip->C & 7) { vpb_set_error("%s: skip channels %d not a multiple of 8", sk.c_str(), skip->C); return VPB_ERR_ARG; }
+    C2 = skip->C;
+  }
+  if (Cout & 15) { vpb_set_error("%s: Cout %d not a multiple of 16", dk.c_str(), Cout); return VPB_ERR_ARG; }
+  // fp32 parameters -> device scratch, composed operands in fp32, then rounded to the 16-bit storage type
+  std::vector<void*> tmp;
+  auto put = [&](const std::vector<float>& v) -> float* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(v.size() * 4, 256)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    tmp.push_back(d);
+    cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
+    return static_cast<float*>(d);
+  };
+  auto scratch = [&](size_t n) -> float* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(n * 4, 256)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    tmp.push_back(d);
+    return static_cast<float*>(d);
+  };
+  auto done = [&](int rc) { for (void* d : tmp) cudaFree(d); return rc; };
+  const size_t nwf = static_cast<size_t>(16) * Cout * Cin, nw2 = static_cast<size_t>(9) * Cout * C2;
+  float *d_w3 = put(w3->f), *d_b3 = put(b3->f), *d_wt = put(ut->f), *d_bt = put(ub->f);
+  float *d_ws = st ? put(st->f) : nullptr, *d_bs = sb ? put(sb->f) : nullptr;
+  float *d_wf = scratch(nwf), *d_w2f = C2 ? scratch(nw2) : nullptr;
+  float* d_b9 = static_cast<float*>(e.dalloc(static_cast<size_t>(9) * Cout * 4, true));
+  void* d_wf16 = e.dalloc(nwf * 2, true);
+  void* d_w216 = C2 ? e.dalloc(nw2 * 2, true) : nullptr;
+  if (!d_w3 || !d_b3 || !d_wt || !d_bt || (st && (!d_ws || !d_bs)) || !d_wf || (C2 && !d_w2f) || !d_b9 || !d_wf16 || (C2 && !d_w216)) {
+    if (!e.oom) vpb_set_error("%s: device allocation for the weight composition failed", dk.c_str());
+    e.oom = true;
+    return done(VPB_ERR_CUDA);
+  }
+  int rc = vpb_upconv_compose(d_w3, d_b3, d_wt, d_bt, d_ws, d_bs, Cout, Cmid, Cin, C2, d_wf, d_w2f, d_b9, e.stream);
+  if (rc == VPB_OK) rc = vpb_f32_to_16(e.dtype, d_wf, d_wf16, static_cast<long long>(nwf), e.stream);
+  if (rc == VPB_OK && C2) rc = vpb_f32_to_16(e.dtype, d_w2f, d_w216, static_cast<long long>(nw2), e.stream);
+  if (cudaStreamSynchronize(e.stream) != cudaSuccess && rc == VPB_OK) { vpb_set_error("%s: weight composition failed", dk.c_str()); rc = VPB_ERR_CUDA; }
+  if (rc != VPB_OK) return done(rc);
+  done(VPB_OK);
+  *out = e.act_alloc(in.H * 2, in.W * 2, (Cout + 7) / 8 * 8, /*pad=*/1);
+  rc = e.add_conv(tag + "up" + std::to_string(i) + "dec" + std::to_string(dec), in, Cout, 4, 4, d_wf16, d_b9, ACT_GELU,
+                  VPB_EPI_STORE, out, nullptr, 0, nullptr, nullptr, skip, d_w216, C2 ? 9 : 0);
+  if (rc == VPB_OK)   // what the reference's three layers cost: ConvTranspose + skip 1x1 at 4 phases, then the 3x3 at 2H x 2W
+    e.ops.back().flops_ref = 2.0 * in.H * in.W * 4.0 * Cmid * (Cin + C2) + 2.0 * (4.0 * in.H * in.W) * Cout * 9.0 * Cmid;
+  return rc;
+}
+
 // SceneContext / DepthContext / AutoSteerContext (scene_context.py:25-57)
 static int build_context(vp_engine& e, const WeightMap& w, const std::string& p, const std::string& tag,
                          const Tens& feat, Tens* ctx) {
@@ -549,11 +623,17 @@ static int build_neck(vp_engine& e, const WeightMap& w, const std::string& p, co
   Tens d = ctx, u;
   const int skip_src[3] = {3, 2, 1};
   for (int b = 0; b < 3; ++b) {
-    int rc = up_skip(e, w, p, b, tag, d, &enc.f[skip_src[b]], &u);
-    if (rc) return rc;
     Tens a, c;
-    rc = conv_layer(e, w, p + "decode_layer_" + std::to_string(2 * b), tag + "dec" + std::to_string(2 * b), u, 9, ACT_GELU, VPB_EPI_STORE, &a, nullptr);
-    if (rc) return rc;
+    int rc;
+    if (upconv_enabled(e)) {
+      rc = upconv_layer(e, w, p, b, 2 * b, tag, d, &enc.f[skip_src[b]], &a);
+      if (rc) return rc;
+    } else {
+      rc = up_skip(e, w, p, b, tag, d, &enc.f[skip_src[b]], &u);
+      if (rc) return rc;
+      rc = conv_layer(e, w, p + "decode_layer_" + std::to_string(2 * b), tag + "dec" + std::to_string(2 * b), u, 9, ACT_GELU, VPB_EPI_STORE, &a, nullptr);
+      if (rc) return rc;
+    }
     rc = conv_layer(e, w, p + "decode_layer_" + std::to_string(2 * b + 1), tag + "dec" + std::to_string(2 * b + 1), a, 9, ACT_GELU, VPB_EPI_STORE, &c, nullptr);
     if (rc) return rc;
     d = c;
@@ -596,11 +676,17 @@ static int build_head(vp_engine& e, const WeightMap& w, const std::string& p, co
     return final_conv(e, w, p + "decode_layer_8", tag + "dec8", b, VPB_FINAL_EGOLANES, mo);
   }
   Tens u3, a, b, u4, c, d;
-  rc = up_skip(e, w, p, 3, tag, neck, &enc.f[0], &u3); if (rc) return rc;
-  rc = conv_layer(e, w, p + "decode_layer_6", tag + "dec6", u3, 9, ACT_GELU, VPB_EPI_STORE, &a, nullptr); if (rc) return rc;
-  rc = conv_layer(e, w, p + "decode_layer_7", tag + "dec7", a, 9, ACT_GELU, VPB_EPI_STORE, &b, nullptr); if (rc) return rc;
-  rc = up_skip(e, w, p, 4, tag, b, nullptr, &u4); if (rc) return rc;
-  rc = conv_layer(e, w, p + "decode_layer_8", tag + "dec8", u4, 9, ACT_GELU, VPB_EPI_STORE, &c, nullptr); if (rc) return rc;
+  if (upconv_enabled(e)) {
+    rc = upconv_layer(e, w, p, 3, 6, tag, neck, &enc.f[0], &a); if (rc) return rc;
+    rc = conv_layer(e, w, p + "decode_layer_7", tag + "dec7", a, 9, ACT_GELU, VPB_EPI_STORE, &b, nullptr); if (rc) return rc;
+    rc = upconv_layer(e, w, p, 4, 8, tag, b, nullptr, &c); if (rc) return rc;
+  } else {
+    rc = up_skip(e, w, p, 3, tag, neck, &enc.f[0], &u3); if (rc) return rc;
+    rc = conv_layer(e, w, p + "decode_layer_6", tag + "dec6", u3, 9, ACT_GELU, VPB_EPI_STORE, &a, nullptr); if (rc) return rc;
+    rc = conv_layer(e, w, p + "decode_layer_7", tag + "dec7", a, 9, ACT_GELU, VPB_EPI_STORE, &b, nullptr); if (rc) return rc;
+    rc = up_skip(e, w, p, 4, tag, b, nullptr, &u4); if (rc) return rc;
+    rc = conv_layer(e, w, p + "decode_layer_8", tag + "dec8", u4, 9, ACT_GELU, VPB_EPI_STORE, &c, nullptr); if (rc) return rc;
+  }
   rc = conv_layer(e, w, p + "decode_layer_9", tag + "dec9", c, 9, ACT_GELU, VPB_EPI_STORE, &d, nullptr); if (rc) return rc;
   e.taps[tag + "d9"] = d;
   const int fk = kind == VP_SCENE_SEG ? VPB_FINAL_ARGMAX : kind == VP_DOMAIN_SEG ? VPB_FINAL_THRESH : VPB_FINAL_NONE;
@@ -924,6 +1010,7 @@ extern "C" int vp_engine_get_stats(const vp_engine* e, vp_engine_stats* s) {
   s->n_launches = static_cast<int>(e->ops.size()) + 1;
   for (const auto& op : e->ops) {
     s->total_flops += op.flops;
+    s->reference_flops += op.flops_ref >= 0 ? op.flops_ref : op.flops;
     if (op.gemm) { ++s->n_gemm_launches; s->gemm_flops += op.flops; }
   }
   s->weight_bytes = e->weight_bytes; s->act_bytes = e->act_bytes;

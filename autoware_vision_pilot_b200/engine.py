@@ -33,7 +33,7 @@ class _Output(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [("n_launches", C.c_int), ("n_gemm_launches", C.c_int), ("gemm_flops", C.c_double),
                 ("total_flops", C.c_double), ("weight_bytes", C.c_size_t), ("act_bytes", C.c_size_t),
-                ("shared_encoders", C.c_int), ("shared_trunks", C.c_int)]
+                ("shared_encoders", C.c_int), ("shared_trunks", C.c_int), ("reference_flops", C.c_double)]
 
 
 class _TapView(C.Structure):

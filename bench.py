@@ -68,7 +68,7 @@ def load_traffic():
 
 
 TENSOR_KERNELS = ("conv_gemm_kernel", "conv3x3_lin_kernel", "conv3x3_pair_kernel", "conv3x3_splitk_kernel",
-                  "convt_ws_kernel")
+                  "convt_ws_kernel", "upconv_pair_kernel")
 
 
 def stage_rooflines(eng, peaks):

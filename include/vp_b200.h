@@ -108,11 +108,14 @@ typedef struct {
   int n_launches;        /* kernels launched per frame                                           */
   int n_gemm_launches;   /* of which tcgen05 implicit-GEMM convolutions                          */
   double gemm_flops;     /* algorithmic 2*MAC of those convolutions per frame                    */
-  double total_flops;    /* algorithmic 2*MAC per frame of everything executed (shared parts once) */
+  double total_flops;    /* 2*MAC per frame actually EXECUTED (shared parts once; the fused ConvTranspose->Conv3x3
+                            layers run fewer MACs than the reference's two layers)                */
   size_t weight_bytes;   /* device bytes of packed weights                                       */
   size_t act_bytes;      /* device bytes of activation buffers                                   */
   int shared_encoders;   /* number of encoder evaluations saved by weight-equality sharing       */
   int shared_trunks;     /* number of context+neck evaluations saved                             */
+  double reference_flops; /* 2*MAC per frame of the REFERENCE's layer-by-layer graph for the same work (SURVEY.md 8d:
+                            1153.25 GFLOP for the shared-encoder four-task frame)                */
 } vp_engine_stats;
 int vp_engine_get_stats(const vp_engine* e, vp_engine_stats* s);
 /* Eagerly run one frame with a CUDA-event pair around every kernel; returns the per-kernel

@@ -48,7 +48,7 @@ void vpb_set_error(const char* fmt, ...);
 /* Implicit-GEMM convolution on tcgen05 tensor cores.
  *   taps = 9 : Conv2d 3x3 stride 1 pad 1   (scene_neck.py:13-24, scene_seg_head.py:13-19, ...)
  *   taps = 1 : Conv2d 1x1                  (skip links scene_neck.py:12, EfficientNet pointwise)
- *   phases = 4 (taps must be 1): ConvTranspose2d k2 s2 (scene_neck.py:11); phase p=(a*2+b)
+ *   phases = 4, taps = 1: ConvTranspose2d k2 s2 (scene_neck.py:11); phase p=(a*2+b)
  *              writes output pixel (2h+a, 2w+b); out/res then have spatial size 2H x 2W.
  *   w      : [taps*phases][Cout][Cin] 16-bit,   bias: fp32 [Cout] or NULL
  *   in     : [H][W][ldi]  (Cin valid channels, ldi >= Cin, both multiples of 8)
@@ -119,8 +119,27 @@ typedef struct {
   const void* res_lo;
   const void* in2_lo;
   const void* w2_lo;
+  /* "upconv" (taps == 4, phases == 4, TILE algorithm): ConvTranspose2d(k2,s2) [+ Conv1x1(skip)] followed by Conv3x3
+   * + bias + act as ONE GEMM over the LOW-resolution input (scene_neck.py:30-37, scene_seg_head.py:25-33: no activation
+   * between the two layers, so they compose exactly).  in is [H][W][Cin] (low res), out [2H][2W][Cout];
+   *   w     [phase(a*2+b)*4 + tap(ty*2+tx)][Cout][Cin]: output pixel (2h+a, 2w+b) += w . in[h+ty-1+a][w+tx-1+b]
+   *   in2   (optional) the skip tensor at OUTPUT resolution, taps2 must be 9, w2 [dy*3+dx][Cout][Cin2]
+   *   bias  fp32 [9][Cout]: row (cy*3 + cx), cy/cx = 0 first, 1 interior, 2 last output row / column (the folded
+   *         ConvTranspose bias only passes through the 3x3 taps that lie inside the image)
+   * vpb_upconv_compose builds w / w2 / bias from the three layers' parameters.  mode STORE, act NONE | GELU. */
+  int taps2;
 } vpb_conv_args;
 int vpb_conv_gemm(const vpb_conv_args* a, void* stream);
+/* Composition of the upconv operands on the device (all pointers device fp32, outputs may be NULL to skip):
+ *   w3 [Cout][Cmid][3][3], b3 [Cout]          Conv2d 3x3            (e.g. decode_layer_0, scene_neck.py:13)
+ *   wt [Cin][Cmid][2][2],  bt [Cmid]          ConvTranspose2d k2 s2 (upsample_layer_0, scene_neck.py:11)
+ *   ws [Cmid][C2],         bs [Cmid]          Conv2d 1x1 skip link  (skip_link_layer_0, scene_neck.py:12) or NULL, C2 = 0
+ *   -> wf [16][Cout][Cin], w2f [9][Cout][C2], bias9 [9][Cout] as vpb_conv_args describes. */
+int vpb_upconv_compose(const float* w3, const float* b3, const float* wt, const float* bt, const float* ws,
+                       const float* bs, int Cout, int Cmid, int Cin, int C2, float* wf, float* w2f, float* bias9,
+                       void* stream);
+/* fp32 -> 16-bit (dtype VPB_F16 | VPB_BF16) conversion of n device values, round to nearest even */
+int vpb_f32_to_16(int dtype, const float* src, void* dst, long long n, void* stream);
 
 /* ---- fused pre-process (resize + /255 + normalise + HWC uint8 -> [320][640][4] 16-bit) ----
  * resize_mode: how the caller's frame is brought to 640x320

@@ -179,7 +179,10 @@ def test_multitask_shares_subgraphs_and_matches_single_engines(ckpt, frame0):
     st = mt.stats()
     assert st["shared_encoders"] == 2 and st["shared_trunks"] == 1
     # algorithmic FLOPs/frame of the shared graph (1 153.25 G)
-    assert abs(st["total_flops"] / 1e9 - 1153.25) < 2.0
+    # the graph stands for the reference's whole four-task frame and executes fewer MACs than it: the
+    # ConvTranspose -> Conv3x3 pairs run as one composed GEMM over the low-resolution tensor
+    assert abs(st["reference_flops"] / 1e9 - 1153.25) < 2.0
+    assert 700.0 < st["total_flops"] / 1e9 < 800.0
     mt.infer(frame)
     for i, m in enumerate(net.MODELS):
         single = E.Engine([kinds[i]], [paths[i]], resize_mode=E.RESIZE_PIL_BICUBIC)
