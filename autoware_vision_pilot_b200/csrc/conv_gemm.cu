@@ -61,6 +61,7 @@ namespace vpb {
 static constexpr int kEpiWarps = 16;
 static constexpr int kThreads = 64 + kEpiWarps * 32;
 static constexpr int kMaxStages = 8;
+static constexpr int kUpcStages = 12;       // upconv_pair_kernel ring (stages of 20-32 KB)
 static constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 ch x 2 B
 static constexpr int kAccStride = 256;         // TMEM columns between the two accumulators
 // 227 KB opt-in limit covers static + dynamic shared memory; keep 4 KB for the static part.
@@ -245,22 +246,27 @@ __device__ __forceinline__ void epilogue_chunks(const ConvKParams& p, uint32_t t
 // inside the loop.
 // ACT: ACT_NONE | ACT_GELU | ACT_SILU (the encoder's expand / head convolutions); ADD: residual added after the
 // activation (MBConv projection + skip: out = conv + bias + res), the whole N tile inside the residual row as well.
-template <class E, int ACT, bool ADD = false>
+// CLS / gb: as epilogue_to_smem — a border pixel of the upconv kernel reads its bias row from global memory.
+template <class E, int ACT, bool ADD = false, bool CLS = false>
 __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32_t t_row, int n0,
-                                                    const float* sbias, int part, const EpiPix& px) {
+                                                    const float* sbias, int part, const EpiPix& px,
+                                                    const float* gb = nullptr) {
   const int nchunks = p.BN >> 4;
   typename E::T* op = reinterpret_cast<typename E::T*>(p.out) + (px.ooff + n0 + part * 16);
   const typename E::T* rp = ADD ? reinterpret_cast<const typename E::T*>(p.res) + (px.roff + n0 + part * 16) : nullptr;
   const float4* sb4 = reinterpret_cast<const float4*>(sbias + part * 16);
+  const float4* gb4 = (CLS && gb) ? reinterpret_cast<const float4*>(gb + part * 16) : nullptr;
   uint32_t ta = t_row + part * 16;
   const bool ok = px.ok, zero = px.zero;
-  auto finish = [&](const uint32_t (&rr)[16], const float4* sb, typename E::T* o, const typename E::T* r) {
+  auto finish = [&](const uint32_t (&rr)[16], const float4* sb, typename E::T* o, const typename E::T* r, int goff = 0) {
     uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
     if (ADD && ok) { r0 = reinterpret_cast<const uint4*>(r)[0]; r1 = reinterpret_cast<const uint4*>(r)[1]; }   // in flight early
     float2 v[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b4 = sb[i];
+      float4 b4;
+      if (CLS && gb4) b4 = __ldg(gb4 + goff + i);
+      else b4 = sb[i];
       v[2 * i] = fadd2(make_float2(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1])), make_float2(b4.x, b4.y));
       v[2 * i + 1] = fadd2(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(b4.z, b4.w));
     }
@@ -294,8 +300,9 @@ __device__ __forceinline__ void epilogue_store_fast(const ConvKParams& p, uint32
     tmem_ld16(ta + 64, rb);
     tmem_ld_wait();
     finish(ra, sb4, op, rp);
-    finish(rb, sb4 + 16, op + 64, rp + 64);
+    finish(rb, sb4 + 16, op + 64, rp + 64, 16);
     if (ADD) rp += 128;
+    if (CLS && gb4) gb4 += 32;
   }
   if (chunk < nchunks) {
     uint32_t ra[16];
@@ -1471,7 +1478,7 @@ template <class E>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 upconv_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_full[kUpcStages], bar_empty[kUpcStages];
   __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_holder;
 
@@ -1484,7 +1491,8 @@ upconv_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   const uint32_t stage_bytes = kATileBytes + bh_bytes;
   const int nslab = p.BN >> 6;
   const uint32_t slab0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (slab0 - smem_u32(smem_raw)) + nslab * (128 * 128));   // [tiles_n * BN]
+  // tma_store == 0 (direct-store epilogue): no slabs, the ring gets their shared memory
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (slab0 - smem_u32(smem_raw)) + (p.tma_store ? nslab * (128 * 128) : 0));   // [tiles_n * BN]
   const int npt = p.tiles_h * p.tiles_w, npairs = (npt + 1) >> 1;
   const int kc1 = p.kchunks, kc2 = p.kchunks2;
 
@@ -1635,6 +1643,24 @@ upconv_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       mbar_wait(smem_u32(&bar_tfull[as]), aphase);
       tc_fence_after();
       if (tr && gleader && slab == 0 && it < 8) p.trace[it * 16 + 10] = clock64();
+      if (!p.tma_store) {
+        // direct stores from registers: slower per tile than the staged TMA store, but hidden behind the next tile's
+        // MMAs (double-buffered accumulators), and the ring is 2-4 stages deeper without the slabs
+        const int oh = 2 * h + pa, ow = 2 * w + pb, Wo = 2 * p.W;
+        EpiPix px;
+        px.ok = (h < p.H) && (w < p.W) && (pt < npt);
+        px.zero = false;
+        px.ooff = static_cast<uint32_t>((oh + p.out_pad) * (Wo + 2 * p.out_pad) + (ow + p.out_pad)) * p.ldo;
+        px.roff = 0; px.fpix = 0;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+        if (p.act == ACT_GELU) epilogue_store_fast<E, ACT_GELU, false, true>(p, t_row, n0, s_bias + n0, part, px, gb);
+        else epilogue_store_fast<E, ACT_NONE, false, true>(p, t_row, n0, s_bias + n0, part, px, gb);
+        tc_fence_before();
+        __syncwarp();
+        if (tr && gleader && slab == 0 && it < 8) p.trace[it * 16 + 12] = clock64();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&bar_tempty[as]), 0);
+        continue;
+      }
       if (gleader) bulk_wait_read0();          // this slab's previous store has read the shared memory
       named_bar_sync(2 + slab, gthreads);
       if (tr && gleader && slab == 0 && it < 8) p.trace[it * 16 + 11] = clock64();
@@ -1651,7 +1677,7 @@ upconv_pair_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       }
       if (lane == 0) mbar_arrive_cluster(smem_u32(&bar_tempty[as]), 0);
     }
-    if (gleader) { bulk_wait0(); if (tr && slab == 0) p.trace[253] = clock64(); }
+    if (gleader && p.tma_store) { bulk_wait0(); if (tr && slab == 0) p.trace[253] = clock64(); }
   }
 
   tc_fence_before();
@@ -1967,7 +1993,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     const size_t stage_bytes = kATileBytes + b_bytes * (p.fuse4 ? 4 : 1);
     // staged TMA-store epilogue: plain store (ConvTranspose, with or without the fused skip link) or GELU, N tile made
     // of whole 64-channel slabs; dbg_gb == 2 forces the direct-store epilogue (A/B comparison)
-    p.tma_store = (p.wstat || p.upc || (!split && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) && p.BN % 64 == 0 &&
+    p.tma_store = (p.wstat || (p.upc && (a->dbg_gb == 3 || a->Cout % p.BN)) || (!split && a->mode == VPB_EPI_STORE && (a->act == ACT_NONE || a->act == ACT_GELU) && p.BN % 64 == 0 &&
                                a->phases == 4 && a->dbg_gb != 2)) ? 1 : 0;
     const size_t slab_bytes = p.tma_store ? static_cast<size_t>(p.BN / 64) * 128 * 128 : 0;
     int stages = static_cast<int>((kMaxDynSmem - 1024 - slab_bytes) / stage_bytes);
@@ -1975,7 +2001,7 @@ int conv_plan_build(const vpb_conv_args* a, ConvPlan* plan) {
     if (p.upc) {
       const size_t st = kATileBytes + static_cast<size_t>(p.BN / 2) * 128, bias_b = (static_cast<size_t>(p.tiles_n) * p.BN * 4 + 1023) / 1024 * 1024;
       const long ring = static_cast<long>(kMaxDynSmem) - 1024 - static_cast<long>(slab_bytes) - static_cast<long>(bias_b);
-      p.stages = static_cast<int>(std::min<long>(kMaxStages, ring / static_cast<long>(st)));
+      p.stages = static_cast<int>(std::min<long>(kUpcStages, ring / static_cast<long>(st)));
       if (p.stages < 3) { vpb_set_error("conv: upconv ring does not fit"); return VPB_ERR_ARG; }
       plan->smem_bytes = p.stages * st + slab_bytes + bias_b + 1024;
       p.total_tiles = ((p.tiles_h * p.tiles_w + 1) / 2) * p.tiles_n * 4;      // pixel-tile pairs x (phase, N tile)

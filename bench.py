@@ -2,6 +2,8 @@
 """bench.py — camera frames/s @1080p multi-task on B200 (BASELINE.json metric), one JSON line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py --autospeed ...      # row f.4: the AutoSpeed detector, 1080p frame -> boxes
+    python bench.py --config5 ...        # row e: multi-camera all-gather + fusion, one rank per camera (torchrun)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one 1920x1080 RGB camera frame through the whole hot path: fused pre-process
@@ -15,8 +17,11 @@ Lines printed by rank 0:
   e2e        the same metric through the reference-facing C-ABI call vp_engine_infer with pinned
              HOST frames: H2D of the frame + kernels + D2H of the masks/depth inside the timed
              region; also the p50 / p95 pre-proc->masks latency;
-  roofline   the dominant kernel (tcgen05 implicit-GEMM convolution): algorithmic FLOPs per launch
-             / mean launch duration, measured here with a CUDA-event pair around every launch;
+  roofline   the dominant kernel (the tensor-core kernel with the most device time per frame): 2*MAC it executes per
+             launch / mean launch duration, all its launches of the frame issued back to back for >= 2 s between one
+             CUDA-event pair (vp_engine_time_kernel), against the measured SUSTAINED cuBLAS bf16 peak; for the composed
+             ConvTranspose->Conv3x3 GEMM also in the reference layers' FLOPs (achieved_reference_equivalent);
+             roofline.stages = one entry per kernel of the frame (HBM-bound ones against the measured copy peak);
   cpu_baseline  the oracle (CPU fp32 port of the reference's PyTorch path: PIL resize -> 4 networks
              -> post-process) on the host cores, a bounded sample, N=1 only.
   --impl reference  times that CPU path alone with all host threads (the reference's own
@@ -55,15 +60,16 @@ def load_peaks():
     return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "src": "fallback"}
 
 
-def load_traffic():
-    """Average DRAM bytes per launch of the dominant convolution kernel from the newest committed ncu
-    `--set full` capture (profiles/r*_conv_traffic.json, produced by scripts/ncu_conv_traffic.sh).  STATIC: read
-    from the committed file, not measured in this run (ncu cannot run inside a timed bench)."""
+def load_traffic(kernel):
+    """Average DRAM bytes per launch of the dominant kernel from the newest committed ncu capture of THAT kernel
+    (profiles/r*_traffic*.json, produced by scripts/ncu_conv_traffic.sh).  STATIC: read from the committed file, not
+    measured in this run (ncu cannot run inside a timed bench)."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_traffic.json")))
-    if files:
-        with open(files[-1]) as f:
-            return json.load(f).get("avg_dram_bytes"), os.path.relpath(files[-1], ROOT)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*traffic*.json")), reverse=True):
+        with open(path) as f:
+            d = json.load(f)
+        if d.get("kernel") == kernel:
+            return d.get("avg_dram_bytes"), os.path.relpath(path, ROOT)
     return None, None
 
 
@@ -613,7 +619,11 @@ def main():
     e2e_fps = world * n_e2e_frames / (e2e_ms / 1e3)
     achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak = peaks["tflops_sustained"]
-    traffic, traffic_src = load_traffic()
+    traffic, traffic_src = load_traffic(dom)
+    # FLOPs the reference's layer-by-layer graph spends on what the fused ConvTranspose->Conv3x3 launches compute
+    extra_ref = max(0.0, stats["reference_flops"] - stats["total_flops"]) if dom == "upconv_pair_kernel" else 0.0
+    dom_per_frame = next(r["launches_per_frame"] for r in stages if r["kernel"] == dom)
+    ref_equiv = (gemm_fl + extra_ref * n_gemm / max(dom_per_frame, 1)) / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     line = {
         "metric": "camera frames/sec @1080p multi-task", "value": fps, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / timed_steps, "higher_is_better": True,
@@ -628,7 +638,8 @@ def main():
                    "weights": "seeded synthetic state_dicts (oracle/synth.py)",
                    "l2": f"{POOL_FRAMES} distinct device-resident frames cycled (149 MB > L2); weights+activations "
                          f"{(stats['weight_bytes'] + stats['act_bytes']) / 1e6:.0f} MB",
-                   "gflop_per_frame_algorithmic": GFLOP_MT, "gflop_per_frame_executed": stats["total_flops"] / 1e9,
+                   "gflop_per_frame_algorithmic": GFLOP_MT, "gflop_per_frame_reference_graph": stats["reference_flops"] / 1e9,
+                   "gflop_per_frame_executed": stats["total_flops"] / 1e9,
                    "shared_encoders": stats["shared_encoders"], "shared_trunks": stats["shared_trunks"],
                    "frames_in_flight_per_gpu": n_eng},
         "clocks": clocks,
@@ -640,8 +651,12 @@ def main():
         "gpu_launches": stats["n_launches"] * timed_steps,
         "launches_per_frame": stats["n_launches"],
         "tensor_tflops_whole_step": GFLOP_MT * fps / world / 1e3,
-        "roofline": {"bound": "tensor", "kernel": f"{dom} (tcgen05 implicit-GEMM 3x3 convolution)",
+        "roofline": {"bound": "tensor", "kernel": f"{dom} (tcgen05 implicit-GEMM convolution)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     "flops_counted": "2*MAC the kernel EXECUTES (the composed ConvTranspose->Conv3x3 GEMM runs 44 % of the "
+                                      "reference layers' MACs for the same outputs, DESIGN.md 3e)",
+                     "achieved_reference_equivalent": ref_equiv,
+                     "frac_reference_equivalent": ref_equiv / peak if peak else None,
                      "peak_src": f"{peaks['src']} bf16 cuBLAS, SUSTAINED: the kernel is timed over {gemm_ms / 1e3:.1f} s of "
                                  "back-to-back launches",
                      "frac_vs_burst_peak": achieved / peaks["tflops_burst"] if peaks["tflops_burst"] else None,

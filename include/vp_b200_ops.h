@@ -76,7 +76,8 @@ typedef struct {
   int algo;               /* VPB_ALGO_TILE (default) | VPB_ALGO_LINEAR (3x3 on a padded input:
                              one TMA segment per kernel row serves the three dx taps) */
   int dbg_ms;             /* experiment hook: force 1 or 2 M sub-tiles per CTA in the LINEAR kernel (0 = auto) */
-  int dbg_gb;             /* experiment hook: 1 = one weight tile per pipeline stage in the LINEAR kernel */
+  int dbg_gb;             /* experiment hook: 1 = one weight tile per pipeline stage in the LINEAR kernel; 2 = ConvTranspose
+                             with the direct-store epilogue; 3 = upconv with the staged TMA-store epilogue */
   int dbg_base_offset;    /* experiment hook: also set the descriptor base_offset = dx in the LINEAR
                              kernel (measured WRONG on B200; default 0 is the correct setting) */
   /* Optional second 1x1 input accumulated into the same fp32 accumulator before the epilogue

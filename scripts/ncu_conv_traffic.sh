@@ -1,13 +1,15 @@
 #!/bin/bash
-# DRAM bytes + duration of every launch of the dominant kernel (conv3x3_pair_kernel) in the 4-task frame
-# (one ncu pass with 3 metrics).
-# Writes gpurun_out/conv_traffic.csv and profiles-ready JSON gpurun_out/conv_traffic.json
+# DRAM bytes + duration of every launch of one tensor-core kernel of the 4-task frame (one ncu pass with 3 metrics):
+#   bash scripts/ncu_conv_traffic.sh [kernel-name-regex, default upconv_pair] [launches to skip] [launches to capture]
+# Writes gpurun_out/conv_traffic.csv and the profiles-ready JSON gpurun_out/conv_traffic.json
 mkdir -p gpurun_out
+KERNEL=${1:-upconv_pair}; SKIP=${2:-60}; COUNT=${3:-60}
+export KERNEL
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-   -k regex:'conv3x3_pair' -s 120 -c 120 --csv --log-file gpurun_out/conv_traffic.csv \
+   -k regex:"$KERNEL" -s $SKIP -c $COUNT --csv --log-file gpurun_out/conv_traffic.csv \
    python bench.py --steps 6 --warmup 3 --no-cpu-baseline --inflight 1 > gpurun_out/conv_traffic.log 2>&1
 python - <<'PY'
-import csv, json, collections
+import csv, json, collections, os
 rows = [r for r in csv.reader(open("gpurun_out/conv_traffic.csv")) if len(r) > 10 and r[0].isdigit()]
 by_id = collections.defaultdict(dict)
 for r in rows:
@@ -22,7 +24,7 @@ for k, d in by_id.items():
     v, u = d["gpu__time_duration.sum"]; dur += v * {"ns": 1e-3, "us": 1, "ms": 1e3}.get(u, 1e-3)
 out = {"launches": n, "avg_dram_read_bytes": rd / max(n, 1), "avg_dram_write_bytes": wr / max(n, 1),
        "avg_dram_bytes": (rd + wr) / max(n, 1), "avg_duration_us_under_ncu": dur / max(n, 1),
-       "kernel": "conv3x3_pair_kernel", "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:conv3x3_pair -s 120 -c 120 over bench.py frames (scripts/ncu_conv_traffic.sh)"}
+       "kernel": os.environ["KERNEL"] + "_kernel", "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:%s over whole bench.py frames (scripts/ncu_conv_traffic.sh)" % os.environ["KERNEL"]}
 json.dump(out, open("gpurun_out/conv_traffic.json", "w"), indent=1)
 print(out)
 PY

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Per-launch device times of one benchmark run (cold-cache, serialised: compare SHARES, not absolutes).
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 700 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 9000 -c 700 --csv \
    --log-file gpurun_out/launches.csv python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
 tail -2 gpurun_out/launches_bench.log | cut -c1-300
 python - <<'PY'

@@ -1,5 +1,5 @@
 """Timeline of CTA 0 of upconv_pair_kernel (clock64 stamps through the dbg_trace hook):
-python scripts/trace_upconv.py H W Cin Cout C2 [bn]"""
+python scripts/trace_upconv.py H W Cin Cout C2 [bn [gb]]"""
 import ctypes as C
 import sys
 
@@ -12,6 +12,7 @@ from autoware_vision_pilot_b200 import _lib as L  # noqa: E402
 def main():
     H, W, Cin, Cout, C2 = map(int, sys.argv[1:6])
     bn = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+    gb = int(sys.argv[7]) if len(sys.argv) > 7 else 0     # 3 = staged TMA-store epilogue
     lib = L.lib()
     x = torch.randn(H, W, Cin, device="cuda").half()
     w = (torch.randn(16, Cout, Cin, device="cuda") * 0.02).half()
@@ -21,7 +22,7 @@ def main():
     a = L.ConvArgs()
     a.dtype = L.VPB_F16
     a.H, a.W, a.Cin, a.ldi, a.Cout, a.taps, a.phases = H, W, Cin, Cin, Cout, 4, 4
-    a.act, a.bn = L.ACT_GELU, bn
+    a.act, a.bn, a.dbg_gb = L.ACT_GELU, bn, gb
     a.inp, a.w, a.bias, a.out, a.ldo = x.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), Cout
     if C2:
         s = torch.randn(2 * H, 2 * W, C2, device="cuda").half()

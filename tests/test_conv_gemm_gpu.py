@@ -130,7 +130,7 @@ def test_conv_transpose_phases(H, W, Cin, Cout):
     (20, 40, 96, 72, 40, 0, 0),        # K tails on both inputs, N tail
     (40, 80, 64, 256, 24, 1, 1),       # zero-bordered skip tensor
     (80, 160, 256, 256, 16, 0, 1),     # up3 of the SceneSeg head at full size (skip = f0, 16 ch): weight-stationary pair kernel, N tile 256
-    (40, 80, 512, 512, 24, 0, 1),      # upsample_layer_2 of the neck (skip = f1): weight-stationary pair kernel, N tile 128
+    (40, 80, 512, 512, 24, 0, 1),      # upsample_layer_2 of the neck (skip = f1): 9 K chunks x 13 tile pairs -> stays on the tile kernel (plan heuristic)
     (80, 160, 256, 200, 32, 1, 1),     # weight-stationary kernel with an N tail and a zero-bordered skip tensor
     (20, 40, 768, 768, 40, 0, 1),      # upsample_layer_1 (7 pixel tiles: an odd count, the last pair is half empty)
     (36, 52, 128, 128, 16, 0, 0),      # ragged pixel tiles

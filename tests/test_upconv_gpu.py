@@ -100,6 +100,7 @@ def _emulate(x, s, wf16, w2f16, b9, act):
     return out.permute(1, 2, 0)
 
 
+@pytest.mark.parametrize("gb", [0, 3], ids=["direct_store", "tma_store"])
 @pytest.mark.parametrize("H,W,Cin,Cmid,Cout,C2,bn,pads,dtype,act", [
     (10, 20, 128, 128, 128, 0, 0, 0, L.VPB_F16, L.ACT_GELU),
     (20, 40, 256, 256, 256, 32, 0, 0, L.VPB_F16, L.ACT_GELU),      # skip link, N tile 256
@@ -109,7 +110,7 @@ def _emulate(x, s, wf16, w2f16, b9, act):
     (9, 17, 64, 64, 128, 0, 64, 0, L.VPB_F16, L.ACT_GELU),         # odd sizes: odd number of pixel tiles in a pair
     (20, 40, 128, 128, 128, 32, 0, 0, L.VPB_BF16, L.ACT_GELU),
 ])
-def test_upconv_matches_two_layer_reference(H, W, Cin, Cmid, Cout, C2, bn, pads, dtype, act):
+def test_upconv_matches_two_layer_reference(H, W, Cin, Cmid, Cout, C2, bn, pads, dtype, act, gb):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     from tests.gpu_util import conv_gemm, pad_img, tdtype
@@ -134,7 +135,7 @@ def test_upconv_matches_two_layer_reference(H, W, Cin, Cmid, Cout, C2, bn, pads,
     w2f16 = w2f.to(td) if C2 else None
     _, _, out = conv_gemm(pad_img(x) if pads else x, wf16, b9, taps=4, phases=4, act=act, dtype=dtype, bn=bn,
                           in_pad=pads, out_pad=pads, in2=(pad_img(s) if pads else s) if C2 else None, w2=w2f16,
-                          in2_pad=pads, taps2=9 if C2 else 0)
+                          in2_pad=pads, taps2=9 if C2 else 0, gb=gb)
     if pads:
         assert (out[0].float() == 0).all() and (out[-1].float() == 0).all()
         assert (out[:, 0].float() == 0).all() and (out[:, -1].float() == 0).all()
