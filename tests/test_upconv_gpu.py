@@ -109,6 +109,8 @@ def _emulate(x, s, wf16, w2f16, b9, act):
     (20, 40, 192, 128, 256, 40, 128, 1, L.VPB_F16, L.ACT_NONE),    # K tail (192 = 3 chunks), forced N tile 128, no activation
     (9, 17, 64, 64, 128, 0, 64, 0, L.VPB_F16, L.ACT_GELU),         # odd sizes: odd number of pixel tiles in a pair
     (20, 40, 128, 128, 128, 32, 0, 0, L.VPB_BF16, L.ACT_GELU),
+    (10, 20, 72, 64, 64, 80, 0, 1, L.VPB_F16, L.ACT_GELU),         # K tails on both inputs: Cin = 64 + 8, C2 = 64 + 16 (f3 of the encoder)
+    (10, 20, 320, 256, 768, 80, 0, 1, L.VPB_F16, L.ACT_GELU),      # three N tiles of 256 (decode_layer_0 has Cout = 768), one pixel-tile pair
 ])
 def test_upconv_matches_two_layer_reference(H, W, Cin, Cmid, Cout, C2, bn, pads, dtype, act, gb):
     torch.backends.cudnn.allow_tf32 = False
