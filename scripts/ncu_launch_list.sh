@@ -1,5 +1,6 @@
 #!/bin/bash
 # Per-launch device times of one benchmark run (cold-cache, serialised: compare SHARES, not absolutes).
+# NOTE: the skip count passes ~9000 launches (engine construction incl. the load-time weight composition) through ncu: ~8 min of box time.
 mkdir -p gpurun_out
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 9000 -c 700 --csv \
    --log-file gpurun_out/launches.csv python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
