@@ -449,7 +449,7 @@ def main():
     ap.add_argument("--autospeed", action="store_true", help="SURVEY 8f.4: the AutoSpeed detector instead of the 4-task frame")
     ap.add_argument("--min-seconds", type=float, default=1.0,
                     help="the K-step block is repeated inside the timed region until it lasts at least this long")
-    ap.add_argument("--inflight", type=int, default=3,
+    ap.add_argument("--inflight", type=int, default=4,
                     help="camera frames in flight per GPU (engine replicas on separate streams; the next "
                          "frame's latency-bound encoder overlaps the current frame's decoders)")
     args = ap.parse_args()

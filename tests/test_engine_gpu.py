@@ -7,8 +7,8 @@ accumulate; all versus the fp32 oracle on the identical uint8 input):
   * resized uint8 image                bit-exact
   * normalised tensor                  within 1 fp16 ulp
   * logits / depth                     max |d| <= 0.075 sigma, mean |d| <= 0.005 sigma  (fp16)
-                                       max |d| <= 0.65  sigma, mean |d| <= 0.055 sigma  (bf16: measured
-                                       0.49 / 0.044; 8-bit mantissa, optional mode)
+                                       max |d| <= 0.235 sigma, mean |d| <= 0.0152 sigma (bf16: 1.25 x the measured
+                                       0.187 / 0.0121; 8-bit mantissa, optional mode)
   * integer maps (argmax, >0 masks)    100 % equal wherever the oracle margin exceeds
                                        tau = 2 * max|d logit|; overall mismatch fraction < 0.5 %
 """
@@ -24,7 +24,7 @@ from oracle import net, resize, synth
 
 pytestmark = pytest.mark.gpu
 
-GATE = {"fp16": (0.075, 0.005), "bf16": (0.65, 0.055)}
+GATE = {"fp16": (0.075, 0.005), "bf16": (0.235, 0.0152)}
 
 
 @pytest.fixture(scope="module")
