@@ -6,7 +6,7 @@
 //   nn.Conv2d 1x1         scene_neck.py:12,17,22 (skip links) and EfficientNet-B0 pointwise convs
 //   nn.ConvTranspose2d k2 s2   scene_neck.py:11,16,21, scene_seg_head.py:11,16
 //
-// Four main loops share one epilogue.
+// Six main loops share one epilogue family.
 //
 // (1) conv_gemm_kernel — "tile" formulation, any of the three op types.
 //     Activations are NHWC 16-bit.  For an output tile of 128 pixels (a TH x TW patch) and BN
@@ -38,6 +38,13 @@
 // (4) conv3x3_splitk_kernel — formulation (2) with the K chunks of one output tile divided over a
 //     cluster of 2-4 CTAs; fp32 partials are reduced through distributed shared memory in rank order
 //     (deterministic).  Used for the 10x20 context layers (<= 32 output tiles, 36-72 K groups).
+//
+// (5) convt_ws_kernel — weight-stationary ConvTranspose (+ skip) on a CTA pair; since (6) only on the layer-by-layer
+//     graphs (VPB_UPCONV=0, split-fp16 mode falls back to (1)).
+//
+// (6) upconv_pair_kernel — ConvTranspose2d(k2,s2) [+ Conv1x1 skip] and the Conv3x3 + GELU that follows, composed into
+//     ONE GEMM over the low-resolution tensor (weights from upconv_compose.cu): four 2x2 taps per output phase + nine
+//     skip taps, CTA pair, M = 256.  Dominant by device time in the 16-bit engines.
 //
 // All: operands land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma reads
 // through descriptors; fp32 accumulators in TMEM, two of them, so the epilogue of tile i overlaps
