@@ -70,6 +70,17 @@ def test_conv_rejects_bad_arguments_without_a_gpu():
     a.Cin = a.ldi = 16
     a.taps = 4
     assert lib.vpb_conv_gemm(C.byref(a), None) == -1
+    # upconv (taps = 4, phases = 4): the [9][Cout] bias, Cout % 16 and the skip tap count are checked before any device work
+    a.phases, a.Cout = 4, 32
+    assert lib.vpb_conv_gemm(C.byref(a), None) == -1 and "upconv" in L.last_error()      # no bias
+    dummy = (C.c_float * (9 * 32))()
+    a.bias = C.addressof(dummy)
+    a.Cout = 24
+    assert lib.vpb_conv_gemm(C.byref(a), None) == -1 and "upconv" in L.last_error()      # Cout not a multiple of 16
+    a.Cout, a.in2, a.w2, a.Cin2, a.ld2, a.taps2 = 32, C.addressof(dummy), C.addressof(dummy), 8, 8, 1
+    assert lib.vpb_conv_gemm(C.byref(a), None) == -1 and "upconv" in L.last_error()      # skip taps must be 9
+    lib.vpb_upconv_compose.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p] * 4
+    assert lib.vpb_upconv_compose(None, None, None, None, None, None, 8, 8, 8, 0, None, None, None, None) == -1
 
 
 def test_vpw_writer_layout(tmp_path):
