@@ -561,6 +561,9 @@ static int upconv_layer(vp_engine& e, const WeightMap& w, const std::string& p, 
     e.oom = true;
     return done(VPB_ERR_CUDA);
   }
+  // the parameter uploads above are pageable-memory copies on the legacy stream: they have only been STAGED when cudaMemcpy
+  // returns, and e.stream does not synchronise with the legacy stream — wait for them before the first kernel reads them
+  if (cudaDeviceSynchronize() != cudaSuccess) { vpb_set_error("%s: upload of the layer parameters failed", dk.c_str()); return done(VPB_ERR_CUDA); }
   int rc = vpb_upconv_compose(d_w3, d_b3, d_wt, d_bt, d_ws, d_bs, Cout, Cmid, Cin, C2, d_wf, d_w2f, d_b9, e.stream);
   if (rc == VPB_OK) rc = vpb_f32_to_16(e.dtype, d_wf, d_wf16, static_cast<long long>(nwf), e.stream);
   if (rc == VPB_OK && C2) rc = vpb_f32_to_16(e.dtype, d_w2f, d_w216, static_cast<long long>(nw2), e.stream);
